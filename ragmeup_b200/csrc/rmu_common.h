@@ -1,0 +1,50 @@
+// Host-side helpers shared by the translation units of libragmeup_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda.h>
+#include <stdint.h>
+#include <atomic>
+#include <string>
+
+#include "../../include/ragmeup_b200.h"
+
+namespace rmu {
+
+void set_error(const std::string& msg);
+extern std::atomic<uint64_t> g_launches;
+
+// every kernel launch in the library goes through this counter (bench.py gpu_launches)
+inline void count_launch(int n = 1) { g_launches.fetch_add(static_cast<uint64_t>(n), std::memory_order_relaxed); }
+
+#define RMU_CUDA(expr)                                                                       \
+    do {                                                                                     \
+        cudaError_t _e = (expr);                                                             \
+        if (_e != cudaSuccess) {                                                             \
+            ::rmu::set_error(std::string(#expr) + ": " + cudaGetErrorString(_e));            \
+            return RMU_ERR_CUDA;                                                             \
+        }                                                                                    \
+    } while (0)
+
+#define RMU_CHECK_LAUNCH()                                                                   \
+    do {                                                                                     \
+        cudaError_t _e = cudaGetLastError();                                                 \
+        if (_e != cudaSuccess) {                                                             \
+            ::rmu::set_error(std::string("kernel launch: ") + cudaGetErrorString(_e));       \
+            return RMU_ERR_CUDA;                                                             \
+        }                                                                                    \
+    } while (0)
+
+// cuTensorMapEncodeTiled resolved through the runtime (no link-time libcuda dependency, so the
+// library loads on a GPU-less build box).  Returns nullptr + sets the error when unavailable.
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+PFN_encodeTiled get_encode_tiled();
+
+// 2-D row-major [rows, cols] tensor of `elem_bytes` elements, box {box_cols, box_rows}, 128-B swizzle.
+int make_tmap_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t row_stride_bytes,
+                 uint32_t box_cols, uint32_t box_rows, int elem_bytes);
+
+int device_sm_count();
+
+}  // namespace rmu

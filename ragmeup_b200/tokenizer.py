@@ -1,0 +1,118 @@
+"""Host-side WordPiece tokenisation.
+
+The reference tokenises with HuggingFace ``tokenizers`` (Rust) through
+``BertTokenizerFast`` inside sentence-transformers (called from
+``server/RAGHelper_local.py:114-117`` / ``server/RAGHelper.py:484``); it is not
+GPU arithmetic and stays on the host here too, using the same library.  This
+module only builds the ``tokenizers.Tokenizer`` (from a snapshot's
+``tokenizer.json`` / ``vocab.txt`` or a seeded synthetic vocab) and packs
+batches into the ragged ``cu_seqlens`` layout the CUDA encoder consumes
+(no padding tokens are ever sent to the device).
+"""
+from __future__ import annotations
+
+import os
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+from tokenizers import Tokenizer, models, normalizers, pre_tokenizers, processors, decoders
+
+PAD, UNK, CLS, SEP, MASK = 0, 100, 101, 102, 103
+
+_SYL = ["ba", "ce", "di", "fo", "gu", "ha", "je", "ki", "lo", "mu", "na", "pe", "qi", "ro", "su",
+        "ta", "ve", "wi", "xo", "yu", "za", "bri", "cle", "dro", "fla", "gri", "ple", "sto", "tru", "vla"]
+
+
+def synthetic_vocab(size: int = 30522, seed: int = 7) -> Dict[str, int]:
+    """bert-base-uncased-like id layout ([PAD]=0, [UNK]=100, [CLS]=101, [SEP]=102,
+    [MASK]=103) filled with seeded pseudo-words and ##suffixes."""
+    assert size >= 400
+    vocab: Dict[str, int] = {}
+    specials = {PAD: "[PAD]", UNK: "[UNK]", CLS: "[CLS]", SEP: "[SEP]", MASK: "[MASK]"}
+    i = 0
+    u = 0
+    while i < 104:
+        if i in specials:
+            vocab[specials[i]] = i
+        else:
+            vocab[f"[unused{u}]"] = i
+            u += 1
+        i += 1
+    for ch in "abcdefghijklmnopqrstuvwxyz0123456789.,;:!?'\"()-":
+        vocab[ch] = i
+        i += 1
+    for ch in "abcdefghijklmnopqrstuvwxyz0123456789":
+        vocab["##" + ch] = i
+        i += 1
+    rng = np.random.default_rng(seed)
+    while i < size:
+        n = int(rng.integers(1, 4))
+        word = "".join(_SYL[int(j)] for j in rng.integers(0, len(_SYL), n))
+        if rng.random() < 0.25:
+            word = "##" + word
+        if word not in vocab:
+            vocab[word] = i
+            i += 1
+    return vocab
+
+
+def build_wordpiece(vocab: Dict[str, int], lowercase: bool = True) -> Tokenizer:
+    tok = Tokenizer(models.WordPiece(vocab=vocab, unk_token="[UNK]", max_input_chars_per_word=100))
+    tok.normalizer = normalizers.BertNormalizer(clean_text=True, handle_chinese_chars=True,
+                                                strip_accents=None, lowercase=lowercase)
+    tok.pre_tokenizer = pre_tokenizers.BertPreTokenizer()
+    tok.post_processor = processors.TemplateProcessing(
+        single="[CLS] $A [SEP]", pair="[CLS] $A [SEP] $B:1 [SEP]:1",
+        special_tokens=[("[CLS]", vocab["[CLS]"]), ("[SEP]", vocab["[SEP]"])])
+    tok.decoder = decoders.WordPiece(prefix="##")
+    return tok
+
+
+def load_tokenizer(source: Optional[str], vocab_size: int = 30522) -> Tokenizer:
+    """``source`` = snapshot dir (tokenizer.json or vocab.txt) or None -> synthetic vocab."""
+    if source is None:
+        return build_wordpiece(synthetic_vocab(vocab_size))
+    tj = os.path.join(source, "tokenizer.json")
+    if os.path.exists(tj):
+        return Tokenizer.from_file(tj)
+    vt = os.path.join(source, "vocab.txt")
+    if os.path.exists(vt):
+        with open(vt, encoding="utf-8") as f:
+            vocab = {line.rstrip("\n"): i for i, line in enumerate(f)}
+        return build_wordpiece(vocab)
+    raise FileNotFoundError(f"{source}: neither tokenizer.json nor vocab.txt")
+
+
+def synthetic_sentences(vocab: Dict[str, int], n: int, min_words: int, max_words: int, seed: int) -> List[str]:
+    """Seeded pseudo-sentences made of whole vocabulary words (for tests / benches)."""
+    words = [w for w in vocab if not w.startswith("[") and not w.startswith("##") and len(w) > 1]
+    rng = np.random.default_rng(seed)
+    out = []
+    for _ in range(n):
+        k = int(rng.integers(min_words, max_words + 1))
+        out.append(" ".join(words[int(j)] for j in rng.integers(0, len(words), k)))
+    return out
+
+
+def encode_ragged(tok: Tokenizer, texts_a: Sequence[str], texts_b: Optional[Sequence[str]],
+                  max_length: int) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+    """Tokenise with truncation='longest_first', NO padding, and pack.
+
+    Returns (ids int32 [T], type_ids int32 [T], cu_seqlens int32 [B+1])."""
+    tok.enable_truncation(max_length=max_length, strategy="longest_first")
+    tok.no_padding()
+    if texts_b is None:
+        enc = tok.encode_batch(list(texts_a))
+    else:
+        enc = tok.encode_batch(list(zip(texts_a, texts_b)))
+    lens = np.fromiter((len(e.ids) for e in enc), dtype=np.int64, count=len(enc))
+    cu = np.zeros(len(enc) + 1, dtype=np.int32)
+    np.cumsum(lens, out=cu[1:])
+    total = int(cu[-1])
+    ids = np.empty(total, dtype=np.int32)
+    typ = np.empty(total, dtype=np.int32)
+    for e, o in zip(enc, cu[:-1]):
+        n = len(e.ids)
+        ids[o:o + n] = e.ids
+        typ[o:o + n] = e.type_ids
+    return ids, typ, cu
