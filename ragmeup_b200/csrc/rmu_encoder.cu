@@ -1,11 +1,593 @@
-// placeholder until the encoder lands (keeps every symbol of include/ragmeup_b200.h exported)
-#include "rmu_common.h"
-extern "C" {
-int rmu_encoder_create(const rmu_bert_config*, const float* const*, int, int, rmu_encoder**) { rmu::set_error("encoder not built yet"); return RMU_ERR_UNSUPPORTED; }
-void rmu_encoder_destroy(rmu_encoder*) {}
-int rmu_encoder_embed(rmu_encoder*, const int32_t*, const int32_t*, const int32_t*, int, int, int, int, int, float*, void*) { return RMU_ERR_UNSUPPORTED; }
-int rmu_encoder_classify(rmu_encoder*, const int32_t*, const int32_t*, const int32_t*, int, int, int, float*, void*) { return RMU_ERR_UNSUPPORTED; }
-int rmu_encoder_hidden(rmu_encoder*, const int32_t*, const int32_t*, const int32_t*, int, int, int, float*, void*) { return RMU_ERR_UNSUPPORTED; }
-int rmu_encoder_embed_host(rmu_encoder*, const int32_t*, const int32_t*, const int32_t*, int, int, int, int, int, float*, void*) { return RMU_ERR_UNSUPPORTED; }
-int rmu_encoder_classify_host(rmu_encoder*, const int32_t*, const int32_t*, const int32_t*, int, int, int, float*, void*) { return RMU_ERR_UNSUPPORTED; }
+// Post-LN BERT encoder forward for sm_100a: sentence embeddings and cross-encoder logits.
+//
+// Stands behind HuggingFaceEmbeddings.embed_documents / embed_query (reference call sites
+// server/RAGHelper_local.py:114-117, server/RAGHelper_cloud.py:101-103; arithmetic = transformers
+// BertModel + sentence-transformers Pooling/Normalize) and behind
+// HuggingFaceCrossEncoder.score (server/RAGHelper.py:484, server/ScoredCrossEncoderReranker.py:42;
+// BertForSequenceClassification, H8-H9).  SURVEY.md §8 rows a2-a5, a9, a10.
+//
+// Batches are RAGGED (cu_seqlens): no padding token is ever computed.  The reference pads to the
+// longest sequence of each 32-batch and masks padded keys with finfo.min, which contributes exactly
+// 0 to every softmax, so the packed computation returns the same numbers.
+//
+// Activations between kernels are split fp16 planes (see rmu_gemm.cuh); LayerNorm, softmax, GELU,
+// residual adds, pooling and the classifier head are fp32.
+#include <mutex>
+#include <vector>
+
+#include "rmu_gemm.cuh"
+
+namespace rmu {
+
+// ------------------------------------------------------------------------------------ small kernels
+__global__ void split_planes_kernel(const float* __restrict__ src, __half* __restrict__ hi, __half* __restrict__ lo, size_t n) {
+    size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < n) {
+        __half h, l;
+        split_f16(src[i], h, l);
+        hi[i] = h;
+        lo[i] = l;
+    }
 }
+
+constexpr int kMaxPerLane = 32;  // hidden <= 1024
+
+// LayerNorm of one row held as v[i] = x[lane + 32 i]; biased variance, eps inside the sqrt (nn.LayerNorm)
+__device__ __forceinline__ void warp_layernorm_store(float (&v)[kMaxPerLane], int per_lane, int H, float eps,
+                                                     const float* __restrict__ g, const float* __restrict__ b,
+                                                     __half* __restrict__ hi, __half* __restrict__ lo) {
+    const unsigned lane = lane_id();
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < kMaxPerLane; ++i) if (i < per_lane) s += v[i];
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s / static_cast<float>(H);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < kMaxPerLane; ++i) if (i < per_lane) { const float d = v[i] - mean; q = fmaf(d, d, q); }
+    for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    const float rstd = 1.0f / sqrtf(q / static_cast<float>(H) + eps);
+#pragma unroll
+    for (int i = 0; i < kMaxPerLane; ++i) {
+        if (i < per_lane) {
+            const int d = lane + 32 * i;
+            const float y = (v[i] - mean) * rstd * g[d] + b[d];
+            __half h, l;
+            split_f16(y, h, l);
+            hi[d] = h;
+            lo[d] = l;
+        }
+    }
+}
+
+// word + position + token-type embedding sum -> LayerNorm -> split planes.  One warp per token.
+__global__ void embed_ln_kernel(const int* __restrict__ ids, const int* __restrict__ type_ids,
+                                const int* __restrict__ cu, int B, int T, int H, int vocab, int max_pos, int type_vocab,
+                                const float* __restrict__ word, const float* __restrict__ pos,
+                                const float* __restrict__ typ, const float* __restrict__ g, const float* __restrict__ b,
+                                float eps, __half* __restrict__ hi, __half* __restrict__ lo) {
+    const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (t >= T) return;
+    // sequence of token t: last b with cu[b] <= t
+    int lo_b = 0, hi_b = B;
+    while (hi_b - lo_b > 1) {
+        const int mid = (lo_b + hi_b) >> 1;
+        if (cu[mid] <= t) lo_b = mid; else hi_b = mid;
+    }
+    int p = t - cu[lo_b];
+    p = p < max_pos ? p : max_pos - 1;
+    int id = ids[t];
+    id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
+    int ty = type_ids ? type_ids[t] : 0;
+    ty = ty < 0 ? 0 : (ty >= type_vocab ? type_vocab - 1 : ty);
+    const float* w = word + static_cast<size_t>(id) * H;
+    const float* pp = pos + static_cast<size_t>(p) * H;
+    const float* tt = typ + static_cast<size_t>(ty) * H;
+    const int per_lane = H >> 5;
+    float v[kMaxPerLane];
+#pragma unroll
+    for (int i = 0; i < kMaxPerLane; ++i) {
+        if (i < per_lane) {
+            const int d = lane_id() + 32 * i;
+            v[i] = (w[d] + tt[d]) + pp[d];   // HF: inputs_embeds + token_type_embeddings, then + position
+        }
+    }
+    warp_layernorm_store(v, per_lane, H, eps, g, b, hi + static_cast<size_t>(t) * H, lo + static_cast<size_t>(t) * H);
+}
+
+// LayerNorm(pre) -> split planes.  One warp per token.
+__global__ void ln_kernel(const float* __restrict__ pre, int T, int H, const float* __restrict__ g,
+                          const float* __restrict__ b, float eps, __half* __restrict__ hi, __half* __restrict__ lo) {
+    const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (t >= T) return;
+    const int per_lane = H >> 5;
+    const float* row = pre + static_cast<size_t>(t) * H;
+    float v[kMaxPerLane];
+#pragma unroll
+    for (int i = 0; i < kMaxPerLane; ++i) if (i < per_lane) v[i] = row[lane_id() + 32 * i];
+    warp_layernorm_store(v, per_lane, H, eps, g, b, hi + static_cast<size_t>(t) * H, lo + static_cast<size_t>(t) * H);
+}
+
+// Self-attention of one (sequence, head): softmax(Q K^T / sqrt(dh)) V over the sequence's own
+// tokens, fp32, streaming softmax over key blocks.  thread = query row.
+template <int DH>
+__global__ void __launch_bounds__(128) attention_kernel(const float* __restrict__ qkv, const int* __restrict__ cu,
+                                                        int H, float scale, __half* __restrict__ ctx_hi,
+                                                        __half* __restrict__ ctx_lo) {
+    constexpr int KB = 64;   // keys per smem block
+    __shared__ __align__(16) float Ks[KB * DH];
+    __shared__ __align__(16) float Vs[KB * DH];
+    const int b = blockIdx.x, h = blockIdx.y;
+    const int t0 = cu[b], S = cu[b + 1] - t0;
+    const int ld = 3 * H;
+    const float* base = qkv + static_cast<size_t>(t0) * ld + h * DH;
+    for (int r0 = 0; r0 < S; r0 += blockDim.x) {
+        const int qi = r0 + threadIdx.x;
+        const bool active = qi < S;
+        float q[DH], acc[DH];
+#pragma unroll
+        for (int d = 0; d < DH; d += 4) {
+            float4 v = active ? *reinterpret_cast<const float4*>(base + static_cast<size_t>(qi) * ld + d) : make_float4(0, 0, 0, 0);
+            q[d] = v.x * scale; q[d + 1] = v.y * scale; q[d + 2] = v.z * scale; q[d + 3] = v.w * scale;
+            acc[d] = acc[d + 1] = acc[d + 2] = acc[d + 3] = 0.f;
+        }
+        float m = -INFINITY, l = 0.f;
+        for (int k0 = 0; k0 < S; k0 += KB) {
+            const int nk = min(KB, S - k0);
+            __syncthreads();
+            for (int e = threadIdx.x; e < nk * (DH / 4); e += blockDim.x) {
+                const int j = e / (DH / 4), d4 = e % (DH / 4);
+                const float* rowp = base + static_cast<size_t>(k0 + j) * ld + d4 * 4;
+                *reinterpret_cast<float4*>(&Ks[j * DH + d4 * 4]) = *reinterpret_cast<const float4*>(rowp + H);
+                *reinterpret_cast<float4*>(&Vs[j * DH + d4 * 4]) = *reinterpret_cast<const float4*>(rowp + 2 * H);
+            }
+            __syncthreads();
+            if (active) {
+                for (int j0 = 0; j0 < nk; j0 += 16) {
+                    float s[16];
+                    float bm = m;
+#pragma unroll
+                    for (int jj = 0; jj < 16; ++jj) {
+                        const int j = j0 + jj;
+                        float a = -INFINITY;
+                        if (j < nk) {
+                            a = 0.f;
+                            const float4* kr = reinterpret_cast<const float4*>(&Ks[j * DH]);
+#pragma unroll
+                            for (int d4 = 0; d4 < DH / 4; ++d4) {
+                                const float4 kv = kr[d4];
+                                a = fmaf(q[d4 * 4], kv.x, a); a = fmaf(q[d4 * 4 + 1], kv.y, a);
+                                a = fmaf(q[d4 * 4 + 2], kv.z, a); a = fmaf(q[d4 * 4 + 3], kv.w, a);
+                            }
+                        }
+                        s[jj] = a;
+                        bm = fmaxf(bm, a);
+                    }
+                    const float corr = expf(m - bm);   // m = -inf on the first block -> 0
+                    l *= corr;
+#pragma unroll
+                    for (int d = 0; d < DH; ++d) acc[d] *= corr;
+                    m = bm;
+#pragma unroll
+                    for (int jj = 0; jj < 16; ++jj) {
+                        const int j = j0 + jj;
+                        if (j < nk) {
+                            const float pj = expf(s[jj] - m);
+                            l += pj;
+                            const float4* vr = reinterpret_cast<const float4*>(&Vs[j * DH]);
+#pragma unroll
+                            for (int d4 = 0; d4 < DH / 4; ++d4) {
+                                const float4 vv = vr[d4];
+                                acc[d4 * 4] = fmaf(pj, vv.x, acc[d4 * 4]); acc[d4 * 4 + 1] = fmaf(pj, vv.y, acc[d4 * 4 + 1]);
+                                acc[d4 * 4 + 2] = fmaf(pj, vv.z, acc[d4 * 4 + 2]); acc[d4 * 4 + 3] = fmaf(pj, vv.w, acc[d4 * 4 + 3]);
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        if (active) {
+            const float inv = 1.0f / l;
+            const size_t o = static_cast<size_t>(t0 + qi) * H + h * DH;
+#pragma unroll
+            for (int d = 0; d < DH; d += 2) {
+                __half h0, l0, h1, l1;
+                split_f16(acc[d] * inv, h0, l0);
+                split_f16(acc[d + 1] * inv, h1, l1);
+                *reinterpret_cast<__half2*>(ctx_hi + o + d) = __halves2half2(h0, h1);
+                *reinterpret_cast<__half2*>(ctx_lo + o + d) = __halves2half2(l0, l1);
+            }
+        }
+    }
+}
+
+// sentence-transformers Pooling (mean | cls) + optional Normalize -> out [B, H]
+__global__ void __launch_bounds__(256) pool_kernel(const __half* __restrict__ hi, const __half* __restrict__ lo,
+                                                   const int* __restrict__ cu, int H, int mode, int normalize,
+                                                   float* __restrict__ out) {
+    __shared__ float red[32];
+    const int b = blockIdx.x;
+    const int t0 = cu[b], S = cu[b + 1] - t0;
+    float ss = 0.f;
+    float vals[4];   // H <= 1024 with 256 threads
+    int nv = 0;
+    for (int d = threadIdx.x; d < H; d += blockDim.x, ++nv) {
+        float v = 0.f;
+        if (mode == RMU_POOL_CLS) {
+            if (S > 0) v = __half2float(hi[static_cast<size_t>(t0) * H + d]) + __half2float(lo[static_cast<size_t>(t0) * H + d]);
+        } else {
+            for (int t = 0; t < S; ++t) {
+                const size_t o = static_cast<size_t>(t0 + t) * H + d;
+                v += __half2float(hi[o]) + __half2float(lo[o]);
+            }
+            v = v / fmaxf(static_cast<float>(S), 1e-9f);
+        }
+        vals[nv] = v;
+        ss = fmaf(v, v, ss);
+    }
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+    __syncthreads();
+    float tot = 0.f;
+    for (int i = 0; i < (blockDim.x >> 5); ++i) tot += red[i];
+    const float inv = normalize ? 1.0f / fmaxf(sqrtf(tot), 1e-12f) : 1.0f;
+    nv = 0;
+    for (int d = threadIdx.x; d < H; d += blockDim.x, ++nv) out[static_cast<size_t>(b) * H + d] = vals[nv] * inv;
+}
+
+// BertPooler (tanh(W_p h_cls + b_p)) + classifier -> logits [B, num_labels]
+__global__ void __launch_bounds__(256) cls_head_kernel(const __half* __restrict__ hi, const __half* __restrict__ lo,
+                                                       const int* __restrict__ cu, int H, int num_labels,
+                                                       const float* __restrict__ pw, const float* __restrict__ pb,
+                                                       const float* __restrict__ cw, const float* __restrict__ cb,
+                                                       float* __restrict__ out) {
+    extern __shared__ float sh[];   // h[H], pooled[H]
+    float* hcls = sh;
+    float* pooled = sh + H;
+    const int b = blockIdx.x;
+    const size_t o = static_cast<size_t>(cu[b]) * H;
+    for (int d = threadIdx.x; d < H; d += blockDim.x) hcls[d] = __half2float(hi[o + d]) + __half2float(lo[o + d]);
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int j = warp; j < H; j += nw) {
+        const float* wr = pw + static_cast<size_t>(j) * H;
+        float s = 0.f;
+        for (int d = lane_id(); d < H; d += 32) s = fmaf(wr[d], hcls[d], s);
+        for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+        if (lane_id() == 0) pooled[j] = tanhf(s + pb[j]);
+    }
+    __syncthreads();
+    for (int c = warp; c < num_labels; c += nw) {
+        const float* wr = cw + static_cast<size_t>(c) * H;
+        float s = 0.f;
+        for (int d = lane_id(); d < H; d += 32) s = fmaf(wr[d], pooled[d], s);
+        for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+        if (lane_id() == 0) out[static_cast<size_t>(b) * num_labels + c] = s + cb[c];
+    }
+}
+
+__global__ void join_planes_kernel(const __half* __restrict__ hi, const __half* __restrict__ lo, float* __restrict__ out, size_t n) {
+    size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = __half2float(hi[i]) + __half2float(lo[i]);
+}
+
+}  // namespace rmu
+
+using namespace rmu;
+
+struct EncLayer {
+    SplitOperand Wqkv, Wo, W1, W2;
+    float *bqkv = nullptr, *bo = nullptr, *b1 = nullptr, *b2 = nullptr;
+    float *ln1g = nullptr, *ln1b = nullptr, *ln2g = nullptr, *ln2b = nullptr;
+};
+
+struct rmu_encoder {
+    rmu_bert_config cfg{};
+    int has_head = 0, sms = 0, device = 0;
+    std::vector<void*> allocs;
+    float *word = nullptr, *pos = nullptr, *typ = nullptr, *eg = nullptr, *eb = nullptr;
+    std::vector<EncLayer> layers;
+    float *pw = nullptr, *pb = nullptr, *cw = nullptr, *cb = nullptr;
+    // activations
+    int tok_cap = 0, seq_cap = 0;
+    std::vector<void*> act_allocs;
+    SplitOperand X, CTX, X1, FF;
+    float *QKV = nullptr, *PRE = nullptr;
+    int *d_ids = nullptr, *d_typ = nullptr, *d_cu = nullptr;   // staging for the *_host entry points
+    float* d_out = nullptr;
+    size_t d_out_elems = 0;
+    std::mutex mu;
+};
+
+template <typename T>
+static int dev_alloc(std::vector<void*>& keep, T** p, size_t count) {
+    void* q = nullptr;
+    RMU_CUDA(cudaMalloc(&q, std::max<size_t>(count, 1) * sizeof(T)));
+    keep.push_back(q);
+    *p = static_cast<T*>(q);
+    return RMU_OK;
+}
+
+static int upload(rmu_encoder* e, float** dst, const float* src_h, size_t n) {
+    int rc = dev_alloc(e->allocs, dst, n);
+    if (rc != RMU_OK) return rc;
+    RMU_CUDA(cudaMemcpy(*dst, src_h, n * sizeof(float), cudaMemcpyHostToDevice));
+    return RMU_OK;
+}
+
+// upload a [rows, cols] fp32 weight (optionally a vertical concat of several) as split fp16 planes
+static int upload_split(rmu_encoder* e, SplitOperand* op, const std::vector<const float*>& parts, int rows_each, int cols) {
+    const size_t rows = static_cast<size_t>(rows_each) * parts.size();
+    const size_t n = rows * cols;
+    float* tmp = nullptr;
+    RMU_CUDA(cudaMalloc(reinterpret_cast<void**>(&tmp), n * sizeof(float)));
+    for (size_t i = 0; i < parts.size(); ++i)
+        RMU_CUDA(cudaMemcpy(tmp + i * rows_each * cols, parts[i], static_cast<size_t>(rows_each) * cols * sizeof(float), cudaMemcpyHostToDevice));
+    __half *hi = nullptr, *lo = nullptr;
+    int rc = dev_alloc(e->allocs, &hi, n);
+    if (rc == RMU_OK) rc = dev_alloc(e->allocs, &lo, n);
+    if (rc != RMU_OK) { cudaFree(tmp); return rc; }
+    split_planes_kernel<<<static_cast<unsigned>((n + 255) / 256), 256>>>(tmp, hi, lo, n);
+    count_launch();
+    cudaError_t err = cudaDeviceSynchronize();
+    cudaFree(tmp);
+    if (err != cudaSuccess) { set_error(std::string("split_planes: ") + cudaGetErrorString(err)); return RMU_ERR_CUDA; }
+    return make_split_operand(op, hi, lo, static_cast<int64_t>(rows), cols);
+}
+
+static void free_acts(rmu_encoder* e) {
+    for (void* p : e->act_allocs) cudaFree(p);
+    e->act_allocs.clear();
+    e->tok_cap = 0;
+}
+
+static int ensure_tokens(rmu_encoder* e, int T, int B) {
+    if (T <= e->tok_cap && B + 1 <= e->seq_cap) return RMU_OK;
+    RMU_CUDA(cudaDeviceSynchronize());
+    free_acts(e);
+    const int H = e->cfg.hidden, F = e->cfg.ffn;
+    int cap = std::max(T, 1024);
+    cap = (cap + 127) / 128 * 128;
+    const int scap = std::max(B + 1, 1024);
+    auto planes = [&](SplitOperand* op, int cols) -> int {
+        __half *hi = nullptr, *lo = nullptr;
+        int rc = dev_alloc(e->act_allocs, &hi, static_cast<size_t>(cap) * cols);
+        if (rc == RMU_OK) rc = dev_alloc(e->act_allocs, &lo, static_cast<size_t>(cap) * cols);
+        if (rc != RMU_OK) return rc;
+        RMU_CUDA(cudaMemset(hi, 0, static_cast<size_t>(cap) * cols * sizeof(__half)));
+        RMU_CUDA(cudaMemset(lo, 0, static_cast<size_t>(cap) * cols * sizeof(__half)));
+        return make_split_operand(op, hi, lo, cap, cols);
+    };
+    int rc = planes(&e->X, H);
+    if (rc == RMU_OK) rc = planes(&e->CTX, H);
+    if (rc == RMU_OK) rc = planes(&e->X1, H);
+    if (rc == RMU_OK) rc = planes(&e->FF, F);
+    if (rc == RMU_OK) rc = dev_alloc(e->act_allocs, &e->QKV, static_cast<size_t>(cap) * 3 * H);
+    if (rc == RMU_OK) rc = dev_alloc(e->act_allocs, &e->PRE, static_cast<size_t>(cap) * H);
+    if (rc == RMU_OK) rc = dev_alloc(e->act_allocs, &e->d_ids, static_cast<size_t>(cap));
+    if (rc == RMU_OK) rc = dev_alloc(e->act_allocs, &e->d_typ, static_cast<size_t>(cap));
+    if (rc == RMU_OK) rc = dev_alloc(e->act_allocs, &e->d_cu, static_cast<size_t>(scap));
+    e->d_out_elems = static_cast<size_t>(scap) * std::max(H, e->cfg.num_labels);
+    if (rc == RMU_OK) rc = dev_alloc(e->act_allocs, &e->d_out, e->d_out_elems);
+    if (rc != RMU_OK) { free_acts(e); return rc; }
+    e->tok_cap = cap;
+    e->seq_cap = scap;
+    return RMU_OK;
+}
+
+// the encoder stack: leaves the last hidden state in e->X (split planes)
+static int run_encoder(rmu_encoder* e, const int32_t* ids, const int32_t* type_ids, const int32_t* cu, int B, int T,
+                       int max_seqlen, cudaStream_t st) {
+    const rmu_bert_config& c = e->cfg;
+    const int H = c.hidden, F = c.ffn, DH = H / c.heads;
+    if (max_seqlen > c.max_pos) { set_error("sequence longer than max_position_embeddings"); return RMU_ERR_ARG; }
+    int rc = ensure_tokens(e, T, B);
+    if (rc != RMU_OK) return rc;
+    const int wpb = 8;
+    const unsigned tok_blocks = static_cast<unsigned>((T + wpb - 1) / wpb);
+    embed_ln_kernel<<<tok_blocks, wpb * 32, 0, st>>>(ids, type_ids, cu, B, T, H, c.vocab_size, c.max_pos, c.type_vocab,
+                                                     e->word, e->pos, e->typ, e->eg, e->eb, c.ln_eps, e->X.hi, e->X.lo);
+    count_launch();
+    RMU_CHECK_LAUNCH();
+    const float scale = 1.0f / sqrtf(static_cast<float>(DH));
+    for (int l = 0; l < c.layers; ++l) {
+        EncLayer& L = e->layers[l];
+        GemmParams g{};
+        g.M = T; g.N = 3 * H; g.K = H; g.bias = L.bqkv; g.out_f32 = e->QKV;
+        rc = launch_gemm(GEMM_BIAS_F32, e->X, L.Wqkv, g, e->sms, st);
+        if (rc != RMU_OK) return rc;
+        dim3 ag(static_cast<unsigned>(B), static_cast<unsigned>(c.heads));
+        if (DH == 32) attention_kernel<32><<<ag, 128, 0, st>>>(e->QKV, cu, H, scale, e->CTX.hi, e->CTX.lo);
+        else attention_kernel<64><<<ag, 128, 0, st>>>(e->QKV, cu, H, scale, e->CTX.hi, e->CTX.lo);
+        count_launch();
+        RMU_CHECK_LAUNCH();
+        g = GemmParams{};
+        g.M = T; g.N = H; g.K = H; g.bias = L.bo; g.out_f32 = e->PRE; g.res_hi = e->X.hi; g.res_lo = e->X.lo;
+        rc = launch_gemm(GEMM_BIAS_RESID_F32, e->CTX, L.Wo, g, e->sms, st);
+        if (rc != RMU_OK) return rc;
+        ln_kernel<<<tok_blocks, wpb * 32, 0, st>>>(e->PRE, T, H, L.ln1g, L.ln1b, c.ln_eps, e->X1.hi, e->X1.lo);
+        count_launch();
+        RMU_CHECK_LAUNCH();
+        g = GemmParams{};
+        g.M = T; g.N = F; g.K = H; g.bias = L.b1; g.out_hi = e->FF.hi; g.out_lo = e->FF.lo;
+        rc = launch_gemm(GEMM_BIAS_GELU_SPLIT, e->X1, L.W1, g, e->sms, st);
+        if (rc != RMU_OK) return rc;
+        g = GemmParams{};
+        g.M = T; g.N = H; g.K = F; g.bias = L.b2; g.out_f32 = e->PRE; g.res_hi = e->X1.hi; g.res_lo = e->X1.lo;
+        rc = launch_gemm(GEMM_BIAS_RESID_F32, e->FF, L.W2, g, e->sms, st);
+        if (rc != RMU_OK) return rc;
+        ln_kernel<<<tok_blocks, wpb * 32, 0, st>>>(e->PRE, T, H, L.ln2g, L.ln2b, c.ln_eps, e->X.hi, e->X.lo);
+        count_launch();
+        RMU_CHECK_LAUNCH();
+    }
+    return RMU_OK;
+}
+
+static int check_batch(const rmu_encoder* e, const void* ids, const void* cu, int B, int T, const void* out) {
+    if (!e || !ids || !cu || !out || B <= 0 || T <= 0) { set_error("encoder: bad argument"); return RMU_ERR_ARG; }
+    return RMU_OK;
+}
+
+extern "C" {
+
+int rmu_encoder_create(const rmu_bert_config* cfg, const float* const* w, int n_weights, int has_head, rmu_encoder** out) {
+    if (!cfg || !w || !out) { set_error("rmu_encoder_create: bad argument"); return RMU_ERR_ARG; }
+    const int H = cfg->hidden, F = cfg->ffn, L = cfg->layers;
+    const int expect = 5 + 16 * L + (has_head ? 4 : 0);
+    if (n_weights != expect) { set_error("rmu_encoder_create: expected " + std::to_string(expect) + " weight tensors"); return RMU_ERR_ARG; }
+    if (H % 128 != 0 || F % 128 != 0 || H > 1024 || cfg->heads <= 0 || H % cfg->heads != 0 ||
+        (H / cfg->heads != 32 && H / cfg->heads != 64)) {
+        set_error("rmu_encoder_create: unsupported shape (hidden/ffn multiples of 128, hidden <= 1024, head_dim 32 or 64)");
+        return RMU_ERR_UNSUPPORTED;
+    }
+    rmu_encoder* e = new rmu_encoder();
+    e->cfg = *cfg;
+    e->has_head = has_head;
+    if (cudaGetDevice(&e->device) != cudaSuccess || (e->sms = device_sm_count()) <= 0) {
+        set_error("rmu_encoder_create: no CUDA device (this library has no CPU path)");
+        delete e;
+        return RMU_ERR_CUDA;
+    }
+    int rc = RMU_OK;
+    int i = 0;
+    auto up = [&](float** dst, size_t n) { if (rc == RMU_OK) rc = upload(e, dst, w[i], n); ++i; };
+    up(&e->word, static_cast<size_t>(cfg->vocab_size) * H);
+    up(&e->pos, static_cast<size_t>(cfg->max_pos) * H);
+    up(&e->typ, static_cast<size_t>(cfg->type_vocab) * H);
+    up(&e->eg, H);
+    up(&e->eb, H);
+    e->layers.resize(L);
+    for (int l = 0; l < L && rc == RMU_OK; ++l) {
+        EncLayer& Ly = e->layers[l];
+        const float *qw = w[i], *qb = w[i + 1], *kw = w[i + 2], *kb = w[i + 3], *vw = w[i + 4], *vb = w[i + 5];
+        i += 6;
+        rc = upload_split(e, &Ly.Wqkv, {qw, kw, vw}, H, H);
+        if (rc == RMU_OK) {
+            std::vector<float> bcat(3 * static_cast<size_t>(H));
+            std::copy(qb, qb + H, bcat.begin());
+            std::copy(kb, kb + H, bcat.begin() + H);
+            std::copy(vb, vb + H, bcat.begin() + 2 * H);
+            rc = upload(e, &Ly.bqkv, bcat.data(), bcat.size());
+        }
+        if (rc == RMU_OK) rc = upload_split(e, &Ly.Wo, {w[i]}, H, H);
+        ++i;
+        up(&Ly.bo, H);
+        up(&Ly.ln1g, H);
+        up(&Ly.ln1b, H);
+        if (rc == RMU_OK) rc = upload_split(e, &Ly.W1, {w[i]}, F, H);
+        ++i;
+        up(&Ly.b1, F);
+        if (rc == RMU_OK) rc = upload_split(e, &Ly.W2, {w[i]}, H, F);
+        ++i;
+        up(&Ly.b2, H);
+        up(&Ly.ln2g, H);
+        up(&Ly.ln2b, H);
+    }
+    if (has_head) {
+        up(&e->pw, static_cast<size_t>(H) * H);
+        up(&e->pb, H);
+        up(&e->cw, static_cast<size_t>(cfg->num_labels) * H);
+        up(&e->cb, cfg->num_labels);
+    }
+    if (rc != RMU_OK) { rmu_encoder_destroy(e); return rc; }
+    *out = e;
+    return RMU_OK;
+}
+
+void rmu_encoder_destroy(rmu_encoder* e) {
+    if (!e) return;
+    cudaDeviceSynchronize();
+    free_acts(e);
+    for (void* p : e->allocs) cudaFree(p);
+    delete e;
+}
+
+int rmu_encoder_embed(rmu_encoder* e, const int32_t* ids, const int32_t* type_ids, const int32_t* cu, int B, int T,
+                      int max_seqlen, int pool_mode, int normalize, float* out, void* stream) {
+    int rc = check_batch(e, ids, cu, B, T, out);
+    if (rc != RMU_OK) return rc;
+    if (pool_mode != RMU_POOL_MEAN && pool_mode != RMU_POOL_CLS) { set_error("bad pool_mode"); return RMU_ERR_ARG; }
+    std::lock_guard<std::mutex> g(e->mu);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    rc = run_encoder(e, ids, type_ids, cu, B, T, max_seqlen, st);
+    if (rc != RMU_OK) return rc;
+    pool_kernel<<<B, 256, 0, st>>>(e->X.hi, e->X.lo, cu, e->cfg.hidden, pool_mode, normalize, out);
+    count_launch();
+    RMU_CHECK_LAUNCH();
+    return RMU_OK;
+}
+
+int rmu_encoder_classify(rmu_encoder* e, const int32_t* ids, const int32_t* type_ids, const int32_t* cu, int B, int T,
+                         int max_seqlen, float* out, void* stream) {
+    int rc = check_batch(e, ids, cu, B, T, out);
+    if (rc != RMU_OK) return rc;
+    if (!e->has_head) { set_error("rmu_encoder_classify: encoder was created without a classification head"); return RMU_ERR_ARG; }
+    std::lock_guard<std::mutex> g(e->mu);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    rc = run_encoder(e, ids, type_ids, cu, B, T, max_seqlen, st);
+    if (rc != RMU_OK) return rc;
+    const int H = e->cfg.hidden;
+    cls_head_kernel<<<B, 256, 2 * H * sizeof(float), st>>>(e->X.hi, e->X.lo, cu, H, e->cfg.num_labels, e->pw, e->pb,
+                                                            e->cw, e->cb, out);
+    count_launch();
+    RMU_CHECK_LAUNCH();
+    return RMU_OK;
+}
+
+int rmu_encoder_hidden(rmu_encoder* e, const int32_t* ids, const int32_t* type_ids, const int32_t* cu, int B, int T,
+                       int max_seqlen, float* out, void* stream) {
+    int rc = check_batch(e, ids, cu, B, T, out);
+    if (rc != RMU_OK) return rc;
+    std::lock_guard<std::mutex> g(e->mu);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    rc = run_encoder(e, ids, type_ids, cu, B, T, max_seqlen, st);
+    if (rc != RMU_OK) return rc;
+    const size_t n = static_cast<size_t>(T) * e->cfg.hidden;
+    join_planes_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(e->X.hi, e->X.lo, out, n);
+    count_launch();
+    RMU_CHECK_LAUNCH();
+    return RMU_OK;
+}
+
+static int stage_batch(rmu_encoder* e, const int32_t* ids_h, const int32_t* typ_h, const int32_t* cu_h, int B, int T,
+                       cudaStream_t st) {
+    {
+        std::lock_guard<std::mutex> g(e->mu);
+        int rc = ensure_tokens(e, T, B);
+        if (rc != RMU_OK) return rc;
+    }
+    RMU_CUDA(cudaMemcpyAsync(e->d_ids, ids_h, static_cast<size_t>(T) * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    if (typ_h) RMU_CUDA(cudaMemcpyAsync(e->d_typ, typ_h, static_cast<size_t>(T) * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    RMU_CUDA(cudaMemcpyAsync(e->d_cu, cu_h, static_cast<size_t>(B + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    return RMU_OK;
+}
+
+int rmu_encoder_embed_host(rmu_encoder* e, const int32_t* ids_h, const int32_t* typ_h, const int32_t* cu_h, int B, int T,
+                           int max_seqlen, int pool_mode, int normalize, float* out_h, void* stream) {
+    int rc = check_batch(e, ids_h, cu_h, B, T, out_h);
+    if (rc != RMU_OK) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    rc = stage_batch(e, ids_h, typ_h, cu_h, B, T, st);
+    if (rc != RMU_OK) return rc;
+    rc = rmu_encoder_embed(e, e->d_ids, typ_h ? e->d_typ : nullptr, e->d_cu, B, T, max_seqlen, pool_mode, normalize, e->d_out, st);
+    if (rc != RMU_OK) return rc;
+    RMU_CUDA(cudaMemcpyAsync(out_h, e->d_out, static_cast<size_t>(B) * e->cfg.hidden * sizeof(float), cudaMemcpyDeviceToHost, st));
+    RMU_CUDA(cudaStreamSynchronize(st));
+    return RMU_OK;
+}
+
+int rmu_encoder_classify_host(rmu_encoder* e, const int32_t* ids_h, const int32_t* typ_h, const int32_t* cu_h, int B,
+                              int T, int max_seqlen, float* out_h, void* stream) {
+    int rc = check_batch(e, ids_h, cu_h, B, T, out_h);
+    if (rc != RMU_OK) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    rc = stage_batch(e, ids_h, typ_h, cu_h, B, T, st);
+    if (rc != RMU_OK) return rc;
+    rc = rmu_encoder_classify(e, e->d_ids, typ_h ? e->d_typ : nullptr, e->d_cu, B, T, max_seqlen, e->d_out, st);
+    if (rc != RMU_OK) return rc;
+    RMU_CUDA(cudaMemcpyAsync(out_h, e->d_out, static_cast<size_t>(B) * e->cfg.num_labels * sizeof(float), cudaMemcpyDeviceToHost, st));
+    RMU_CUDA(cudaStreamSynchronize(st));
+    return RMU_OK;
+}
+
+}  // extern "C"

@@ -16,6 +16,7 @@
 //              does not take) run the exact fp32 CUDA-core scan.
 // The ids and scores returned are therefore those of an exact fp32 brute-force search.
 #include <algorithm>
+#include <cstdlib>
 #include <mutex>
 #include <vector>
 
@@ -184,6 +185,7 @@ struct ScanParams {
     const float* rbias;    // nullable (L2)
     unsigned long long* lists;  // [gridDim.x][128][2*KEEP]
     float* dbg;            // diagnostics: CTA 0 dumps the raw accumulators of its first tile [128][BN]
+    int ablate;            // profiling only: bit0 skip MMA issue, bit1 skip epilogue work, bit2 skip TMEM loads
 };
 
 template <int BN, int NBUF, int NSLAB, int KEEP>
@@ -275,7 +277,7 @@ scan_tf32_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
                     const uint64_t bdesc = umma_desc_sw128_kmajor(smem_u32(slabs + slot * SLAB_BYTES));
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
-                        if (kb * 32 + k * 8 < p.dim) {
+                        if (kb * 32 + k * 8 < p.dim && !(p.ablate & 1)) {
                             mma_tf32_ts(d_addr, tmem_base + kb * 32 + k * 8, bdesc + static_cast<uint64_t>(k * 2),
                                         IDESC, (kb | k) != 0 ? 1u : 0u);
                         }
@@ -293,6 +295,7 @@ scan_tf32_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
         unsigned long long* mybuf = p.lists + (static_cast<long long>(blockIdx.x) * kScanQ + qi) * CAP;
         int cnt = 0;
         float tau = live ? -INFINITY : INFINITY;
+        const bool has_sb = (p.rscale != nullptr) || (p.rbias != nullptr);
         for (int t = t0; t < t1; ++t) {
             const int i = t - t0;
             const int buf = i % NBUF;
@@ -301,9 +304,11 @@ scan_tf32_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
             tc_fence_after();
 #pragma unroll 1
             for (int c = 0; c < BN / 32; ++c) {
+                if (p.ablate & 4) break;
                 uint32_t r[32];
                 tmem_ld32(tmem_addr(tmem_base, quad * 32, kScanACols + buf * BN + c * 32), r);
                 tmem_ld_wait();
+                if (p.ablate & 2) continue;
                 const long long row0 = static_cast<long long>(t) * BN + c * 32;
                 if (p.dbg != nullptr && blockIdx.x == 0 && t == t0) {
 #pragma unroll
@@ -311,21 +316,31 @@ scan_tf32_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
                 }
                 if (row0 < p.n) {
                     const int valid = static_cast<int>(min(static_cast<long long>(32), p.n - row0));
-                    if (p.rscale != nullptr || p.rbias != nullptr) {
+                    float key[32];
+                    if (has_sb) {
+                        // per-row scale / bias of this 32-row chunk: one coalesced load, shuffled out
+                        const float sc = (p.rscale != nullptr && static_cast<int>(lane) < valid) ? __ldg(p.rscale + row0 + lane) : 1.f;
+                        const float bi = (p.rbias != nullptr && static_cast<int>(lane) < valid) ? __ldg(p.rbias + row0 + lane) : 0.f;
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            if (j < valid) {
-                                float key = __uint_as_float(r[j]);
-                                if (p.rscale != nullptr) key *= __ldg(p.rscale + row0 + j);
-                                if (p.rbias != nullptr) key += __ldg(p.rbias + row0 + j);
-                                if (key > tau) mybuf[cnt++] = make_key(key, static_cast<uint32_t>(row0 + j));
-                            }
-                        }
+                        for (int j = 0; j < 32; ++j)
+                            key[j] = fmaf(__uint_as_float(r[j]), __shfl_sync(0xffffffffu, sc, j), __shfl_sync(0xffffffffu, bi, j));
                     } else {
 #pragma unroll
+                        for (int j = 0; j < 32; ++j) key[j] = __uint_as_float(r[j]);
+                    }
+                    // branch-free prefilter: most chunks hold nothing above the running threshold
+                    float mx = -INFINITY;
+                    if (valid == 32) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) mx = fmaxf(mx, key[j]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) mx = fmaxf(mx, j < valid ? key[j] : -INFINITY);
+                    }
+                    if (mx > tau) {
+#pragma unroll
                         for (int j = 0; j < 32; ++j) {
-                            const float key = __uint_as_float(r[j]);
-                            if (j < valid && key > tau) mybuf[cnt++] = make_key(key, static_cast<uint32_t>(row0 + j));
+                            if (j < valid && key[j] > tau) mybuf[cnt++] = make_key(key[j], static_cast<uint32_t>(row0 + j));
                         }
                     }
                 }
@@ -790,15 +805,30 @@ static int launch_scan(const CUtensorMap& tmap, const ScanParams& p, int grid, c
     return RMU_OK;
 }
 
-constexpr int kScanBN = 64;
-constexpr int kScanNBUF = 2;
-constexpr int kScanNSLAB = 24;   // 24 x 8 KB = 192 KB of corpus in flight per SM
+// scan tile variants: {rows per tile (MMA N), TMEM accumulator buffers, smem slabs in flight}
+//   0: 64 x 2 buffers, 24 slabs of 8 KB      1: 128 x 1 buffer, 12 slabs of 16 KB
+static int scan_variant() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("RMU_SCAN_VARIANT");
+        v = e ? atoi(e) : 0;
+        if (v < 0 || v > 1) v = 0;
+    }
+    return v;
+}
+static int scan_bn() { return scan_variant() == 1 ? 128 : 64; }
+
+template <int KEEP>
+static int dispatch_variant(const CUtensorMap& tmap, const ScanParams& p, int grid, cudaStream_t st) {
+    if (scan_variant() == 1) return launch_scan<128, 1, 12, KEEP>(tmap, p, grid, st);
+    return launch_scan<64, 2, 24, KEEP>(tmap, p, grid, st);
+}
 
 static int dispatch_scan(int keep, const CUtensorMap& tmap, const ScanParams& p, int grid, cudaStream_t st) {
     switch (keep) {
-        case 64: return launch_scan<kScanBN, kScanNBUF, kScanNSLAB, 64>(tmap, p, grid, st);
-        case 128: return launch_scan<kScanBN, kScanNBUF, kScanNSLAB, 128>(tmap, p, grid, st);
-        case 256: return launch_scan<kScanBN, kScanNBUF, kScanNSLAB, 256>(tmap, p, grid, st);
+        case 64: return dispatch_variant<64>(tmap, p, grid, st);
+        case 128: return dispatch_variant<128>(tmap, p, grid, st);
+        case 256: return dispatch_variant<256>(tmap, p, grid, st);
         default: set_error("scan: unsupported KEEP"); return RMU_ERR_UNSUPPORTED;
     }
 }
@@ -948,20 +978,21 @@ int rmu_index_search(rmu_index* idx, const float* queries, int nq, int k, int64_
     }
 
     if (tensor_ok) {
-        if (idx->tmap_rows != N || idx->tmap_bn != kScanBN) {
+        if (idx->tmap_rows != N || idx->tmap_bn != scan_bn()) {
             rc = make_tmap_2d(&idx->tmap, idx->x, static_cast<uint64_t>(N), static_cast<uint64_t>(D),
-                              static_cast<uint64_t>(D) * sizeof(float), 32, kScanBN, 4);
+                              static_cast<uint64_t>(D) * sizeof(float), 32, scan_bn(), 4);
             if (rc != RMU_OK) return rc;
             idx->tmap_rows = N;
-            idx->tmap_bn = kScanBN;
+            idx->tmap_bn = scan_bn();
         }
-        const int ntiles = static_cast<int>((N + kScanBN - 1) / kScanBN);
+        const int ntiles = static_cast<int>((N + scan_bn() - 1) / scan_bn());
         for (int q0 = 0; q0 < nq; q0 += kScanQ) {
             ScanParams sp{};
             sp.q = queries; sp.q0 = q0; sp.nq = std::min(kScanQ, nq - q0); sp.dim = D; sp.n = N; sp.ntiles = ntiles;
             sp.rscale = idx->metric == RMU_METRIC_COSINE ? idx->rscale : nullptr;
             sp.rbias = idx->metric == RMU_METRIC_L2 ? idx->rbias : nullptr;
             sp.lists = d_scan;
+            { static const char* ab = getenv("RMU_SCAN_ABLATE"); sp.ablate = ab ? atoi(ab) : 0; }
             const int grid = std::min(grid_scan, ntiles);
             rc = dispatch_scan(keep, idx->tmap, sp, grid, st);
             if (rc != RMU_OK) return rc;
@@ -1027,10 +1058,10 @@ int rmu_debug_scan_tile(rmu_index* idx, const float* queries, int nq, float* out
     int rc = ensure_ws(idx, sizeof(unsigned long long) * kScanQ * 2 * 64 + 1024);
     if (rc != RMU_OK) return rc;
     rc = make_tmap_2d(&idx->tmap, idx->x, static_cast<uint64_t>(idx->n), static_cast<uint64_t>(idx->dim),
-                      static_cast<uint64_t>(idx->dim) * sizeof(float), 32, kScanBN, 4);
+                      static_cast<uint64_t>(idx->dim) * sizeof(float), 32, scan_bn(), 4);
     if (rc != RMU_OK) return rc;
     idx->tmap_rows = idx->n;
-    idx->tmap_bn = kScanBN;
+    idx->tmap_bn = scan_bn();
     ScanParams sp{};
     sp.q = queries; sp.q0 = 0; sp.nq = nq; sp.dim = idx->dim; sp.n = idx->n; sp.ntiles = 1;
     sp.lists = static_cast<unsigned long long*>(idx->ws); sp.dbg = out;
