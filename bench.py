@@ -1,0 +1,405 @@
+#!/usr/bin/env python
+"""bench.py — queries/sec of the dense-retrieval hot path (embed -> brute-force top-k -> cross-encoder
+rerank) on a 10M x 384 synthetic corpus, BASELINE.json's metric.
+
+One "step" = one batch of Q queries through the whole path:
+  1. embed      Q query token sequences  -> MiniLM-L6-shaped encoder -> [Q, 384] unit vectors
+  2. top-k      exact top-R (R=100) of every query over this rank's shard of the 10M x 384 fp32 corpus
+  3. merge      (N>1) ONE all-gather of the per-shard [Q, R] candidates over NCCL + on-device merge
+  4. rerank     (query, doc) token pairs of the R candidates -> ms-marco-MiniLM-L-6-shaped cross-encoder
+                -> logits; pairs are split across ranks for N>1 and all-gathered
+  5. select     stable sort by logit, keep top-10 (ScoredCrossEncoderReranker semantics)
+
+`value`   : queries/sec with the step's inputs (query tokens, corpus, doc token table) resident in HBM.
+`e2e`     : same step through the host-buffer C-ABI entry points (rmu_encoder_embed_host,
+            rmu_index_search_host, rmu_encoder_classify_host): token ids / vectors / logits cross PCIe
+            inside the timed region.  Host string tokenisation (HF `tokenizers`, unchanged from the
+            reference) is outside both numbers and outside the CPU arm.
+`--impl reference`: the reference's own CPU path (oracle restatement: torch-CPU fp32 BERT, fp32
+            brute-force top-k, fp32 cross-encoder) on the host cores, bounded sample per step.
+
+Weights are seeded random-init of the named architectures and the corpus is seeded synthetic
+(no network in the image); strong scaling: the corpus is 10M rows in total for every N.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from dataclasses import asdict
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_TOTAL = int(os.environ.get("BENCH_N", 10_000_000))
+DIM = 384
+Q = int(os.environ.get("BENCH_Q", 64))
+R = int(os.environ.get("BENCH_R", 100))        # candidates reranked per query
+TOPN = 10
+Q_TOK = 16                                      # query tokens (without specials)
+D_TOK = 128                                     # doc tokens
+PAIR_LEN = Q_TOK + D_TOK + 3                    # [CLS] q [SEP] d [SEP] = 147
+DOC_TABLE = 65536                               # distinct synthetic documents' token rows
+CHUNK = 250_000                                 # corpus generation granularity (seed per global chunk)
+METRIC = os.environ.get("BENCH_METRIC", "cosine")
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return d.get("hbm_gbs", 6650.0), d.get("bf16_tflops", 1590.0), d.get("bf16_tflops_sustained", 1400.0), "measured"
+    return 6650.0, 1590.0, 1400.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, gpu_index: int):
+        self.rows, self.proc, self.idx = [], None, gpu_index
+
+    def start(self):
+        q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 8:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------- synthetic data
+def corpus_chunk(torch, dev, c: int):
+    g = torch.Generator(device=dev).manual_seed(1000 + c)
+    x = torch.randn(CHUNK, DIM, generator=g, device=dev, dtype=torch.float32)
+    return torch.nn.functional.normalize(x, dim=1)
+
+
+def host_inputs(vocab_size: int):
+    rng = np.random.default_rng(4321)
+    q_tok = rng.integers(104, vocab_size, (Q, Q_TOK)).astype(np.int32)
+    doc_tab = np.random.default_rng(7).integers(104, vocab_size, (DOC_TABLE, D_TOK)).astype(np.int32)
+    return q_tok, doc_tab
+
+
+def query_batch(q_tok: np.ndarray):
+    """[CLS] q [SEP] ragged batch (all the same length here) -> ids, type_ids, cu_seqlens (int32)."""
+    n = q_tok.shape[0]
+    ids = np.concatenate([np.full((n, 1), 101, np.int32), q_tok, np.full((n, 1), 102, np.int32)], 1)
+    cu = (np.arange(n + 1) * ids.shape[1]).astype(np.int32)
+    return ids.reshape(-1), np.zeros(ids.size, np.int32), cu, ids.shape[1]
+
+
+PAIR_TYPES = np.concatenate([np.zeros(Q_TOK + 2, np.int32), np.ones(D_TOK + 1, np.int32)])
+
+
+# ---------------------------------------------------------------------------------------- GPU arm
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    from ragmeup_b200 import _lib
+    from ragmeup_b200.encoder import BertEncoder
+    from ragmeup_b200.index import FlatIndex
+    from ragmeup_b200.sharded import ShardedFlatIndex
+    from ragmeup_b200.weights import PRESETS, BertConfig, synthetic_bert_weights
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    hbm_peak, tf_burst, tf_sust, peak_src = peaks()
+
+    ecfg = BertConfig(**asdict(PRESETS["all-MiniLM-L6-v2"][0]))
+    ccfg = BertConfig(**asdict(PRESETS["ms-marco-MiniLM-L-6-v2"][0]))
+    emb = BertEncoder(ecfg, synthetic_bert_weights(ecfg, seed=0), with_head=False, device=local)
+    ce = BertEncoder(ccfg, synthetic_bert_weights(ccfg, seed=1, with_head=True, scale=4.0), with_head=True, device=local)
+
+    # corpus shard: global chunks [c0, c1)
+    nchunks = N_TOTAL // CHUNK
+    c0, c1 = rank * nchunks // world, (rank + 1) * nchunks // world
+    index = FlatIndex(DIM, METRIC, device=local)
+    index.reserve((c1 - c0) * CHUNK)
+    for c in range(c0, c1):
+        index.add(corpus_chunk(torch, dev, c))
+    sh = ShardedFlatIndex(index)
+    sh.sync_offsets()
+    torch.cuda.synchronize()
+
+    q_tok_h, doc_tab_h = host_inputs(ecfg.vocab_size)
+    q_ids_h, q_typ_h, q_cu_h, q_len = query_batch(q_tok_h)
+    q_ids = torch.from_numpy(q_ids_h).to(dev)
+    q_typ = torch.from_numpy(q_typ_h).to(dev)
+    q_cu = torch.from_numpy(q_cu_h).to(dev)
+    q_tok = torch.from_numpy(q_tok_h).to(dev)
+    doc_tab = torch.from_numpy(doc_tab_h).to(dev)
+    pair_typ_row = torch.from_numpy(PAIR_TYPES).to(dev)
+    cls_col = torch.full((Q, R, 1), 101, dtype=torch.int32, device=dev)
+    sep_col = torch.full((Q, R, 1), 102, dtype=torch.int32, device=dev)
+    npairs = Q * R
+    p0, p1 = rank * npairs // world, (rank + 1) * npairs // world
+    pair_cu = (torch.arange(p1 - p0 + 1, device=dev, dtype=torch.int32) * PAIR_LEN)
+    pair_typ = pair_typ_row.repeat(p1 - p0)
+
+    def step_device():
+        q_emb = emb.embed_tokens(q_ids, q_typ, q_cu, q_len, "mean", True)
+        _, ids = sh.search(q_emb, R)                                   # [Q, R] global ids, best first
+        docs = doc_tab[(ids % DOC_TABLE)]                              # [Q, R, D_TOK]
+        pairs = torch.cat([cls_col, q_tok[:, None, :].expand(Q, R, Q_TOK), sep_col, docs, sep_col], 2)
+        mine = pairs.reshape(npairs, PAIR_LEN)[p0:p1].reshape(-1)
+        logits = ce.classify_tokens(mine, pair_typ, pair_cu, PAIR_LEN)[:, 0]
+        if world > 1:
+            parts = [torch.empty_like(logits) for _ in range(world)]
+            dist.all_gather(parts, logits)
+            logits = torch.cat(parts)
+        order = torch.sort(logits.view(Q, R), dim=1, descending=True, stable=True).indices[:, :TOPN]
+        return torch.gather(ids, 1, order), torch.gather(logits.view(Q, R), 1, order)
+
+    pair_typ_full_h = np.tile(PAIR_TYPES, npairs)
+    pair_cu_full_h = (np.arange(npairs + 1) * PAIR_LEN).astype(np.int32)
+
+    def step_host():
+        """the same step through the host-buffer C-ABI entry points (N = 1 path of the plugin API)"""
+        q_emb = emb.embed_host(q_ids_h, q_typ_h, q_cu_h, "mean", True)
+        _, ids = index.search_host(q_emb, R)
+        docs = doc_tab_h[ids % DOC_TABLE]
+        pairs = np.concatenate([np.full((Q, R, 1), 101, np.int32), np.broadcast_to(q_tok_h[:, None, :], (Q, R, Q_TOK)),
+                                np.full((Q, R, 1), 102, np.int32), docs, np.full((Q, R, 1), 102, np.int32)], 2)
+        logits = ce.classify_host(np.ascontiguousarray(pairs.reshape(-1)), pair_typ_full_h, pair_cu_full_h)[:, 0]
+        order = np.argsort(-logits.reshape(Q, R), axis=1, kind="stable")[:, :TOPN]
+        return np.take_along_axis(ids, order, 1), np.take_along_axis(logits.reshape(Q, R), order, 1)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- timed region: device-resident step
+    for _ in range(args.warmup):
+        out_ids, out_scores = step_device()
+    barrier()
+    launches0 = _lib.launch_count()
+    _lib.profile_reset()
+    _lib.profile_enable(True)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        out_ids, out_scores = step_device()
+    ev1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    total_ms = float(ms.item())
+    _lib.profile_enable(False)
+    prof = _lib.profile_read()
+    launches = _lib.launch_count() - launches0
+
+    # ---------------- e2e through host buffers (rank 0's shard only when N > 1: the host API is per GPU)
+    e2e = None
+    if world == 1:
+        for _ in range(max(1, min(args.warmup, 2))):
+            h_ids, h_scores = step_host()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        n_e2e = max(1, min(args.steps, 5))
+        for _ in range(n_e2e):
+            h_ids, h_scores = step_host()
+        torch.cuda.synchronize()
+        e2e_ms = (time.perf_counter() - t0) * 1e3 / n_e2e
+        same = bool((h_ids == out_ids.cpu().numpy()).all())
+        h2d = q_ids_h.nbytes * 2 + q_cu_h.nbytes + Q * DIM * 4 + npairs * PAIR_LEN * 4 * 2 + pair_cu_full_h.nbytes
+        d2h = Q * DIM * 4 + Q * R * 12 + npairs * 4
+        e2e = {"value": Q / (e2e_ms * 1e-3), "unit": "queries/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(h2d),
+               "d2h_bytes_per_step": int(d2h), "ids_equal_device_path": same,
+               "api": "rmu_encoder_embed_host + rmu_index_search_host + rmu_encoder_classify_host"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    ms_per_step = total_ms / args.steps
+    n_local = (c1 - c0) * CHUNK
+    # rooflines: the dominant kernel of the step is the cross-encoder GEMM (tensor bound);
+    # the top-k scan is the HBM-bound kernel BASELINE.json quotes separately.
+    pairs_local = p1 - p0
+    tok_rerank = pairs_local * PAIR_LEN
+    tok_embed = Q * q_len
+    gemm_flops_per_tok = 2 * ccfg.layers * (4 * ccfg.hidden * ccfg.hidden + 2 * ccfg.hidden * ccfg.ffn)
+    gemm_flops_step = gemm_flops_per_tok * (tok_rerank + tok_embed)
+    gemm_ms, gemm_n = prof["gemm"]
+    scan_ms, scan_n = prof["scan"]
+    roof_gemm = None
+    if gemm_n:
+        ach = gemm_flops_step * args.steps / (gemm_ms * 1e-3) / 1e12
+        roof_gemm = {"kernel": "gemm_f16x3_kernel", "bound": "tensor", "achieved": ach, "peak": tf_sust, "unit": "TFLOP/s",
+                     "frac": ach / tf_sust, "traffic": None, "peak_source": peak_src + " bf16 sustained",
+                     "launches": gemm_n, "avg_launch_ms": gemm_ms / gemm_n,
+                     "note": "algorithmic fp32-equivalent flops; every K step issues 3 fp16 MMAs (hi*hi+lo*hi+hi*lo) to hold 1e-3 fp32 parity, so frac <= 1/3"}
+    roof_scan = None
+    if scan_n:
+        bytes_per_launch = 4.0 * n_local * DIM
+        ach = bytes_per_launch / (scan_ms / scan_n * 1e-3) / 1e9
+        roof_scan = {"kernel": "scan_tf32_kernel", "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
+                     "frac": ach / hbm_peak, "traffic": None, "peak_source": peak_src, "launches": scan_n,
+                     "avg_launch_ms": scan_ms / scan_n, "bytes_per_launch": bytes_per_launch}
+    kernel_ms = {k: round(v[0] / args.steps, 4) for k, v in prof.items() if v[1]}
+
+    cpu = cpu_baseline(sample_queries=2)
+    line = {
+        "metric": "queries/sec (embed+top-k+rerank) on 10M x 384 corpus", "value": Q * world / world / (ms_per_step * 1e-3),
+        "unit": "queries/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32 (fp16 hi/lo split MMA, fp32 accumulate; TF32 coarse scan + exact fp32 re-score)",
+        "data": "synthetic (seeded unit-norm corpus, seeded token ids, random-init MiniLM-L6-shaped encoder and cross-encoder)",
+        "config": {"workload": f"{N_TOTAL}x{DIM} fp32 corpus ({METRIC}), batch {Q} queries x {q_len} tokens, top-{R} -> cross-encoder rerank of {R} pairs x {PAIR_LEN} tokens -> top-{TOPN}",
+                   "corpus_rows_per_gpu": n_local, "parallelism": f"row-sharded corpus x{world}, rerank pairs split x{world}" if world > 1 else "single GPU",
+                   "l2_flush": "not needed: corpus shard (>= 1.9 GB) and activations exceed the 126 MB L2"},
+        "roofline": roof_gemm, "roofline_topk": roof_scan, "kernel_ms_per_step": kernel_ms,
+        "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ---------------------------------------------------------------------------------------- CPU arm
+def cpu_step(sample_queries: int, state: dict):
+    """One bounded sample of the reference CPU path: embed + top-R over a 1M-row block (x10 for the
+    10M corpus, brute force is linear in rows) + cross-encoder rerank, all fp32 on the host cores."""
+    import torch
+    from oracle import bert_ref
+    st = state
+    t = {}
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        h = bert_ref.bert_encoder_forward(st["ew"], st["ecfg"], st["q_ids"][:sample_queries], st["q_mask"][:sample_queries])
+        q_emb = bert_ref.l2_normalize(bert_ref.pool(h, st["q_mask"][:sample_queries], "mean"))
+    t["embed"] = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    ids = []
+    for i in range(sample_queries):                       # the reference searches one query per call
+        sc = st["xblock"] @ q_emb[i]
+        ids.append(torch.topk(sc, R).indices)
+    t["topk_block"] = time.perf_counter() - t0
+    ids = torch.stack(ids)
+    t0 = time.perf_counter()
+    docs = st["doc_tab"][ids % DOC_TABLE]
+    qt = st["q_tok"][:sample_queries]
+    pairs = torch.cat([torch.full((sample_queries, R, 1), 101), qt[:, None, :].expand(sample_queries, R, Q_TOK),
+                       torch.full((sample_queries, R, 1), 102), docs, torch.full((sample_queries, R, 1), 102)], 2).reshape(-1, PAIR_LEN)
+    typ = torch.from_numpy(PAIR_TYPES.astype(np.int64))[None].expand(pairs.shape[0], PAIR_LEN)
+    mask = torch.ones_like(pairs)
+    logits = []
+    with torch.no_grad():
+        for s in range(0, pairs.shape[0], 32):            # CrossEncoder.predict batches of 32
+            hh = bert_ref.bert_encoder_forward(st["cw"], st["ccfg"], pairs[s:s + 32], mask[s:s + 32], typ[s:s + 32])
+            logits.append(bert_ref.classifier_head(st["cw"], hh)[:, 0])
+    t["rerank"] = time.perf_counter() - t0
+    scale = N_TOTAL / st["xblock"].shape[0]
+    total = t["embed"] + t["topk_block"] * scale + t["rerank"]
+    return total, t
+
+
+def cpu_state():
+    import torch
+    from oracle import bert_ref
+    from ragmeup_b200.weights import PRESETS, BertConfig, synthetic_bert_weights
+    torch.set_num_threads(os.cpu_count() or 1)
+    ecfg = BertConfig(**asdict(PRESETS["all-MiniLM-L6-v2"][0]))
+    ccfg = BertConfig(**asdict(PRESETS["ms-marco-MiniLM-L-6-v2"][0]))
+    q_tok_h, doc_tab_h = host_inputs(ecfg.vocab_size)
+    q_ids_h, _, _, q_len = query_batch(q_tok_h)
+    g = torch.Generator().manual_seed(5)
+    xblock = torch.nn.functional.normalize(torch.randn(1_000_000, DIM, generator=g), dim=1)
+    return {"ecfg": bert_ref.BertCfg(**asdict(ecfg)), "ccfg": bert_ref.BertCfg(**asdict(ccfg)),
+            "ew": {k: torch.from_numpy(v) for k, v in synthetic_bert_weights(ecfg, seed=0).items()},
+            "cw": {k: torch.from_numpy(v) for k, v in synthetic_bert_weights(ccfg, seed=1, with_head=True, scale=4.0).items()},
+            "q_ids": torch.from_numpy(q_ids_h.reshape(Q, q_len).astype(np.int64)), "q_mask": torch.ones(Q, q_len, dtype=torch.long),
+            "q_tok": torch.from_numpy(q_tok_h.astype(np.int64)), "doc_tab": torch.from_numpy(doc_tab_h.astype(np.int64)),
+            "xblock": xblock}
+
+
+def cpu_baseline(sample_queries: int = 2, state=None):
+    import torch
+    st = state or cpu_state()
+    cpu_step(1, st)                                       # warm
+    total, t = cpu_step(sample_queries, st)
+    return {"value": sample_queries / total, "unit": "queries/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{sample_queries} queries: embed + top-{R} over a 1M x {DIM} block timed and scaled x{N_TOTAL // 1_000_000} to {N_TOTAL} rows "
+                      f"(brute force is linear in rows) + rerank of {sample_queries * R} pairs x {PAIR_LEN} tokens, torch-CPU fp32 oracle",
+            "seconds": {k: round(v, 4) for k, v in t.items()}}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    st = cpu_state()
+    sample = 2
+    for _ in range(min(args.warmup, 1)):
+        cpu_step(1, st)
+    tot = 0.0
+    for _ in range(args.steps):
+        s, _ = cpu_step(sample, st)
+        tot += s
+    v = sample * args.steps / tot
+    cb = {"value": v, "unit": "queries/s", "cores": torch.get_num_threads(), "kind": "port",
+          "sample": f"each step = {sample} queries (embed + top-{R} over a 1M-row block scaled x{N_TOTAL // 1_000_000} + rerank {sample * R} pairs)"}
+    print(json.dumps({
+        "impl": "reference", "metric": "queries/sec (embed+top-k+rerank) on 10M x 384 corpus", "value": v, "unit": "queries/s",
+        "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": tot / args.steps * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": {"workload": f"{N_TOTAL}x{DIM} fp32 corpus, top-{R} -> rerank {R} pairs x {PAIR_LEN} tokens -> top-{TOPN} (CPU oracle port of the reference path)"},
+        "cpu_baseline": cb, "e2e": {"value": v, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

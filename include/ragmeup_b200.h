@@ -49,6 +49,13 @@ int rmu_version(void);
 /* number of kernels this library has launched in this process (bench.py's gpu_launches) */
 uint64_t rmu_launch_count(void);
 
+/* per-kernel-class device timing (CUDA events on the launching stream; used by bench.py for the
+ * roofline objects).  classes: 0 scan, 1 finalize, 2 exact scan, 3 merge, 4 gemm, 5 attention,
+ * 6 layernorm, 7 embedding, 8 pool/head, 9 misc.  rmu_profile_read synchronises the recorded events. */
+void rmu_profile_enable(int on);
+void rmu_profile_reset(void);
+int rmu_profile_read(int cls, double* total_ms, int64_t* launches);
+
 /* ------------------------------------------------------------------ flat vector index
  * Stands behind the vector store: Milvus.from_documents / PGVector ctor (RAGHelper.py:385-404),
  * db.add_documents (:431,525) and the retriever's col.search (:497-499). */

@@ -31,6 +31,9 @@ SIGNATURES = {
     "rmu_last_error": (C.c_char_p, []),
     "rmu_version": (C.c_int, []),
     "rmu_launch_count": (C.c_uint64, []),
+    "rmu_profile_enable": (None, [C.c_int]),
+    "rmu_profile_reset": (None, []),
+    "rmu_profile_read": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "rmu_index_create": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
     "rmu_index_destroy": (None, [C.c_void_p]),
     "rmu_index_reserve": (C.c_int, [C.c_void_p, C.c_int64]),
@@ -108,3 +111,24 @@ def stream_ptr(torch_stream=None) -> int:
     import torch
     s = torch_stream if torch_stream is not None else torch.cuda.current_stream()
     return int(s.cuda_stream)
+
+
+PROF_CLASSES = ["scan", "finalize", "exact", "merge", "gemm", "attention", "layernorm", "embedding", "pool_head", "misc"]
+
+
+def profile_enable(on: bool) -> None:
+    lib().rmu_profile_enable(int(bool(on)))
+
+
+def profile_reset() -> None:
+    lib().rmu_profile_reset()
+
+
+def profile_read() -> dict:
+    """{class: (total_ms, launches)} since the last reset (synchronises the recorded events)."""
+    out = {}
+    for i, name in enumerate(PROF_CLASSES):
+        ms, n = C.c_double(0), C.c_int64(0)
+        check(lib().rmu_profile_read(i, C.byref(ms), C.byref(n)), "rmu_profile_read")
+        out[name] = (ms.value, int(n.value))
+    return out

@@ -385,8 +385,9 @@ static int run_encoder(rmu_encoder* e, const int32_t* ids, const int32_t* type_i
     if (rc != RMU_OK) return rc;
     const int wpb = 8;
     const unsigned tok_blocks = static_cast<unsigned>((T + wpb - 1) / wpb);
+    { ProfScope _ps(PROF_EMBED, st);
     embed_ln_kernel<<<tok_blocks, wpb * 32, 0, st>>>(ids, type_ids, cu, B, T, H, c.vocab_size, c.max_pos, c.type_vocab,
-                                                     e->word, e->pos, e->typ, e->eg, e->eb, c.ln_eps, e->X.hi, e->X.lo);
+                                                     e->word, e->pos, e->typ, e->eg, e->eb, c.ln_eps, e->X.hi, e->X.lo); }
     count_launch();
     RMU_CHECK_LAUNCH();
     const float scale = 1.0f / sqrtf(static_cast<float>(DH));
@@ -397,15 +398,17 @@ static int run_encoder(rmu_encoder* e, const int32_t* ids, const int32_t* type_i
         rc = launch_gemm(GEMM_BIAS_F32, e->X, L.Wqkv, g, e->sms, st);
         if (rc != RMU_OK) return rc;
         dim3 ag(static_cast<unsigned>(B), static_cast<unsigned>(c.heads));
+        { ProfScope _ps(PROF_ATTN, st);
         if (DH == 32) attention_kernel<32><<<ag, 128, 0, st>>>(e->QKV, cu, H, scale, e->CTX.hi, e->CTX.lo);
-        else attention_kernel<64><<<ag, 128, 0, st>>>(e->QKV, cu, H, scale, e->CTX.hi, e->CTX.lo);
+        else attention_kernel<64><<<ag, 128, 0, st>>>(e->QKV, cu, H, scale, e->CTX.hi, e->CTX.lo); }
         count_launch();
         RMU_CHECK_LAUNCH();
         g = GemmParams{};
         g.M = T; g.N = H; g.K = H; g.bias = L.bo; g.out_f32 = e->PRE; g.res_hi = e->X.hi; g.res_lo = e->X.lo;
         rc = launch_gemm(GEMM_BIAS_RESID_F32, e->CTX, L.Wo, g, e->sms, st);
         if (rc != RMU_OK) return rc;
-        ln_kernel<<<tok_blocks, wpb * 32, 0, st>>>(e->PRE, T, H, L.ln1g, L.ln1b, c.ln_eps, e->X1.hi, e->X1.lo);
+        { ProfScope _ps(PROF_LN, st);
+        ln_kernel<<<tok_blocks, wpb * 32, 0, st>>>(e->PRE, T, H, L.ln1g, L.ln1b, c.ln_eps, e->X1.hi, e->X1.lo); }
         count_launch();
         RMU_CHECK_LAUNCH();
         g = GemmParams{};
@@ -416,7 +419,8 @@ static int run_encoder(rmu_encoder* e, const int32_t* ids, const int32_t* type_i
         g.M = T; g.N = H; g.K = F; g.bias = L.b2; g.out_f32 = e->PRE; g.res_hi = e->X1.hi; g.res_lo = e->X1.lo;
         rc = launch_gemm(GEMM_BIAS_RESID_F32, e->FF, L.W2, g, e->sms, st);
         if (rc != RMU_OK) return rc;
-        ln_kernel<<<tok_blocks, wpb * 32, 0, st>>>(e->PRE, T, H, L.ln2g, L.ln2b, c.ln_eps, e->X.hi, e->X.lo);
+        { ProfScope _ps(PROF_LN, st);
+        ln_kernel<<<tok_blocks, wpb * 32, 0, st>>>(e->PRE, T, H, L.ln2g, L.ln2b, c.ln_eps, e->X.hi, e->X.lo); }
         count_launch();
         RMU_CHECK_LAUNCH();
     }
@@ -511,6 +515,7 @@ int rmu_encoder_embed(rmu_encoder* e, const int32_t* ids, const int32_t* type_id
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     rc = run_encoder(e, ids, type_ids, cu, B, T, max_seqlen, st);
     if (rc != RMU_OK) return rc;
+    ProfScope _ps(PROF_POOL_HEAD, st);
     pool_kernel<<<B, 256, 0, st>>>(e->X.hi, e->X.lo, cu, e->cfg.hidden, pool_mode, normalize, out);
     count_launch();
     RMU_CHECK_LAUNCH();
@@ -527,6 +532,7 @@ int rmu_encoder_classify(rmu_encoder* e, const int32_t* ids, const int32_t* type
     rc = run_encoder(e, ids, type_ids, cu, B, T, max_seqlen, st);
     if (rc != RMU_OK) return rc;
     const int H = e->cfg.hidden;
+    ProfScope _ps(PROF_POOL_HEAD, st);
     cls_head_kernel<<<B, 256, 2 * H * sizeof(float), st>>>(e->X.hi, e->X.lo, cu, H, e->cfg.num_labels, e->pw, e->pb,
                                                             e->cw, e->cb, out);
     count_launch();

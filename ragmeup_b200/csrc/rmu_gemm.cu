@@ -22,6 +22,7 @@ static int launch_mode(const SplitOperand& A, const SplitOperand& W, const GemmP
     }
     const int tiles = ((p.M + kGemmBM - 1) / kGemmBM) * (p.N / kGemmBN);
     const int grid = tiles < sms ? tiles : sms;
+    ProfScope _ps(PROF_GEMM, st);
     kern<<<grid, kGemmThreads, kGemmSmem, st>>>(A.map_hi, A.map_lo, W.map_hi, W.map_lo, p);
     count_launch();
     RMU_CHECK_LAUNCH();

@@ -188,18 +188,21 @@ struct ScanParams {
     int ablate;            // profiling only: bit0 skip MMA issue, bit1 skip epilogue work, bit2 skip TMEM loads
 };
 
-template <int BN, int NBUF, int NSLAB, int KEEP>
+// BN rows per tile (= MMA N), NBUF TMEM accumulators, NSLAB pipeline stages, each stage = KD K-blocks
+// (one TMA op; KD > 1 uses the 3-D (32, rows, kblock) tensor map and needs dim % 32 == 0)
+template <int BN, int NBUF, int NSLAB, int KD, int KEEP>
 __global__ void __launch_bounds__(kScanThreads, 1)
 scan_tf32_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
     constexpr int CAP = 2 * KEEP;
-    constexpr int SLAB_BYTES = BN * 128;
+    constexpr int SLAB_BYTES = BN * 128 * KD;
     constexpr uint32_t IDESC = umma_idesc(2 /*tf32*/, 128, BN);
     static_assert(BN * NBUF <= 512 - kScanACols, "accumulators must fit beside the query block in TMEM");
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* slabs = smem;
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + NSLAB * SLAB_BYTES);
+    float* stage = reinterpret_cast<float*>(smem + NSLAB * SLAB_BYTES);          // [32][128] epilogue staging
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + NSLAB * SLAB_BYTES + 32 * 128 * sizeof(float));
     uint64_t* empty = full + NSLAB;
     uint64_t* acc_full = empty + NSLAB;
     uint64_t* acc_empty = acc_full + NBUF;
@@ -251,10 +254,11 @@ scan_tf32_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
             int slot = 0;
             uint32_t phase = 0;
             for (int t = t0; t < t1; ++t) {
-                for (int kb = 0; kb < KB; ++kb) {
+                for (int kb = 0; kb < KB; kb += KD) {
                     mbar_wait(&empty[slot], phase ^ 1);
                     mbar_arrive_expect_tx(&full[slot], SLAB_BYTES);
-                    tma_load_2d(slabs + slot * SLAB_BYTES, &tmap, kb * 32, t * BN, &full[slot], kEvictFirst);
+                    if (KD == 1) tma_load_2d(slabs + slot * SLAB_BYTES, &tmap, kb * 32, t * BN, &full[slot], kEvictFirst);
+                    else tma_load_3d(slabs + slot * SLAB_BYTES, &tmap, 0, t * BN, kb, &full[slot], kEvictFirst);
                     if (++slot == NSLAB) { slot = 0; phase ^= 1; }
                 }
             }
@@ -271,15 +275,19 @@ scan_tf32_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
                 mbar_wait(&acc_empty[buf], (use & 1) ^ 1);
                 tc_fence_after();
                 const uint32_t d_addr = tmem_base + kScanACols + buf * BN;
-                for (int kb = 0; kb < KB; ++kb) {
+                for (int kb0 = 0; kb0 < KB; kb0 += KD) {
                     mbar_wait(&full[slot], phase);
                     tc_fence_after();
-                    const uint64_t bdesc = umma_desc_sw128_kmajor(smem_u32(slabs + slot * SLAB_BYTES));
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        if (kb * 32 + k * 8 < p.dim && !(p.ablate & 1)) {
-                            mma_tf32_ts(d_addr, tmem_base + kb * 32 + k * 8, bdesc + static_cast<uint64_t>(k * 2),
-                                        IDESC, (kb | k) != 0 ? 1u : 0u);
+                    for (int kk = 0; kk < KD; ++kk) {
+                        const int kb = kb0 + kk;
+                        const uint64_t bdesc = umma_desc_sw128_kmajor(smem_u32(slabs + slot * SLAB_BYTES + kk * (BN * 128)));
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            if (kb * 32 + k * 8 < p.dim && !(p.ablate & 1)) {
+                                mma_tf32_ts(d_addr, tmem_base + kb * 32 + k * 8, bdesc + static_cast<uint64_t>(k * 2),
+                                            IDESC, (kb | k) != 0 ? 1u : 0u);
+                            }
                         }
                     }
                     tc_commit(&empty[slot]);
@@ -291,6 +299,7 @@ scan_tf32_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
     } else {
         // =========================== epilogue: thread = query ===========================
         const int qi = quad * 32 + lane;
+        const int te = qi;                       // this thread's column in the staging buffer
         const bool live = qi < p.nq;
         unsigned long long* mybuf = p.lists + (static_cast<long long>(blockIdx.x) * kScanQ + qi) * CAP;
         int cnt = 0;
@@ -308,6 +317,10 @@ scan_tf32_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
                 uint32_t r[32];
                 tmem_ld32(tmem_addr(tmem_base, quad * 32, kScanACols + buf * BN + c * 32), r);
                 tmem_ld_wait();
+                if (c == BN / 32 - 1) {          // last TMEM read of this tile: hand the accumulator back early
+                    tc_fence_before();
+                    mbar_arrive(&acc_empty[buf]);
+                }
                 if (p.ablate & 2) continue;
                 const long long row0 = static_cast<long long>(t) * BN + c * 32;
                 if (p.dbg != nullptr && blockIdx.x == 0 && t == t0) {
@@ -328,26 +341,30 @@ scan_tf32_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) key[j] = __uint_as_float(r[j]);
                     }
-                    // branch-free prefilter: most chunks hold nothing above the running threshold
-                    float mx = -INFINITY;
-                    if (valid == 32) {
+                    // branch-free pass mask (bit j = row j beats this query's running threshold); the
+                    // insert path is entered warp-uniformly and walks only the set bits, reading the
+                    // scores back from a per-thread smem column (no dynamic register indexing).
+                    unsigned m = 0u;
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) mx = fmaxf(mx, key[j]);
-                    } else {
+                    for (int j = 0; j < 32; ++j) m |= (key[j] > tau) ? (1u << j) : 0u;
+                    if (valid < 32) m &= (1u << valid) - 1u;
+                    if (__any_sync(0xffffffffu, m != 0u)) {
+                        float* col = stage + te;
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) mx = fmaxf(mx, j < valid ? key[j] : -INFINITY);
-                    }
-                    if (mx > tau) {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            if (j < valid && key[j] > tau) mybuf[cnt++] = make_key(key[j], static_cast<uint32_t>(row0 + j));
+                        for (int j = 0; j < 32; ++j) col[j * 128] = key[j];
+                        while (m) {
+                            const int j = __ffs(m) - 1;
+                            m &= m - 1;
+                            mybuf[cnt++] = make_key(col[j * 128], static_cast<uint32_t>(row0 + j));
                         }
                     }
                 }
                 warp_compact<KEEP>(mybuf, cnt, tau, cnt > CAP - 32);
             }
-            tc_fence_before();
-            mbar_arrive(&acc_empty[buf]);
+            if (p.ablate & 4) {
+                tc_fence_before();
+                mbar_arrive(&acc_empty[buf]);
+            }
         }
         // final: every list sorted descending, zero padded to KEEP entries
         warp_compact<KEEP>(mybuf, cnt, tau, true);
@@ -790,38 +807,47 @@ static int keep_for_k(int k) {
     return 256;
 }
 
-template <int BN, int NBUF, int NSLAB, int KEEP>
+template <int BN, int NBUF, int NSLAB, int KD, int KEEP>
 static int launch_scan(const CUtensorMap& tmap, const ScanParams& p, int grid, cudaStream_t st) {
-    auto kern = scan_tf32_kernel<BN, NBUF, NSLAB, KEEP>;
-    const size_t smem = static_cast<size_t>(NSLAB) * BN * 128 + (2 * NSLAB + 2 * NBUF) * 8 + 16 + 1024;
+    auto kern = scan_tf32_kernel<BN, NBUF, NSLAB, KD, KEEP>;
+    const size_t smem = static_cast<size_t>(NSLAB) * BN * 128 * KD + 32 * 128 * sizeof(float) + (2 * NSLAB + 2 * NBUF) * 8 + 16 + 1024;
     static bool attr_set = false;
     if (!attr_set) {
         RMU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
         attr_set = true;
     }
+    ProfScope _ps(PROF_SCAN, st);
     kern<<<grid, kScanThreads, smem, st>>>(tmap, p);
     count_launch();
     RMU_CHECK_LAUNCH();
     return RMU_OK;
 }
 
-// scan tile variants: {rows per tile (MMA N), TMEM accumulator buffers, smem slabs in flight}
-//   0: 64 x 2 buffers, 24 slabs of 8 KB      1: 128 x 1 buffer, 12 slabs of 16 KB
+// scan geometry variants {rows per tile, TMEM accumulators, stages, K-blocks per TMA op}:
+//   0: 64 x 2, 24 x  8 KB (2-D map)      1: 128 x 1, 12 x 16 KB (2-D map)
+//   2: 64 x 2,  6 x 32 KB (3-D map, 4 K-blocks per op)   3: 64 x 2, 12 x 16 KB (3-D, 2 per op)
+//   4: 64 x 2,  4 x 48 KB (3-D, 6 per op)
 static int scan_variant() {
     static int v = -1;
     if (v < 0) {
         const char* e = getenv("RMU_SCAN_VARIANT");
-        v = e ? atoi(e) : 0;
-        if (v < 0 || v > 1) v = 0;
+        v = e ? atoi(e) : 1;
+        if (v < 0 || v > 4) v = 1;
     }
     return v;
 }
 static int scan_bn() { return scan_variant() == 1 ? 128 : 64; }
+static int scan_kd() { const int v = scan_variant(); return v == 2 ? 4 : v == 3 ? 2 : v == 4 ? 6 : 1; }
 
 template <int KEEP>
 static int dispatch_variant(const CUtensorMap& tmap, const ScanParams& p, int grid, cudaStream_t st) {
-    if (scan_variant() == 1) return launch_scan<128, 1, 12, KEEP>(tmap, p, grid, st);
-    return launch_scan<64, 2, 24, KEEP>(tmap, p, grid, st);
+    switch (scan_variant()) {
+        case 1: return launch_scan<128, 1, 12, 1, KEEP>(tmap, p, grid, st);
+        case 2: return launch_scan<64, 2, 6, 4, KEEP>(tmap, p, grid, st);
+        case 3: return launch_scan<64, 2, 12, 2, KEEP>(tmap, p, grid, st);
+        case 4: return launch_scan<64, 2, 4, 6, KEEP>(tmap, p, grid, st);
+        default: return launch_scan<64, 2, 24, 1, KEEP>(tmap, p, grid, st);
+    }
 }
 
 static int dispatch_scan(int keep, const CUtensorMap& tmap, const ScanParams& p, int grid, cudaStream_t st) {
@@ -979,8 +1005,13 @@ int rmu_index_search(rmu_index* idx, const float* queries, int nq, int k, int64_
 
     if (tensor_ok) {
         if (idx->tmap_rows != N || idx->tmap_bn != scan_bn()) {
-            rc = make_tmap_2d(&idx->tmap, idx->x, static_cast<uint64_t>(N), static_cast<uint64_t>(D),
-                              static_cast<uint64_t>(D) * sizeof(float), 32, scan_bn(), 4);
+            if (scan_kd() > 1) {
+                if (D % 32 != 0) { set_error("scan variant needs dim % 32 == 0"); return RMU_ERR_UNSUPPORTED; }
+                rc = make_tmap_rows_kblocks(&idx->tmap, idx->x, static_cast<uint64_t>(N), D / 32, scan_bn(), scan_kd());
+            } else {
+                rc = make_tmap_2d(&idx->tmap, idx->x, static_cast<uint64_t>(N), static_cast<uint64_t>(D),
+                                  static_cast<uint64_t>(D) * sizeof(float), 32, scan_bn(), 4);
+            }
             if (rc != RMU_OK) return rc;
             idx->tmap_rows = N;
             idx->tmap_bn = scan_bn();
@@ -1003,7 +1034,8 @@ int rmu_index_search(rmu_index* idx, const float* queries, int nq, int k, int64_
             fp.k = k; fp.id_offset = id_offset; fp.max_norm_bits = idx->max_norm_bits;
             fp.eps_rel = 2.2e-3f;   // > 2^-9: both TF32 operands truncated to 10 mantissa bits
             fp.out_scores = out_scores; fp.out_ids = reinterpret_cast<long long*>(out_ids); fp.flags = d_flags;
-            finalize_kernel<<<sp.nq, 256, qsmem, st>>>(fp);
+            { ProfScope _ps(PROF_FINALIZE, st);
+            finalize_kernel<<<sp.nq, 256, qsmem, st>>>(fp); }
             count_launch();
             RMU_CHECK_LAUNCH();
         }
@@ -1020,7 +1052,8 @@ int rmu_index_search(rmu_index* idx, const float* queries, int nq, int k, int64_
         int gy = tensor_ok ? 1 : std::min(nq, std::max(1, (2 * idx->sms + nchunks - 1) / nchunks));
         gy = std::min(gy, 65535);
         dim3 eg(static_cast<unsigned>(nchunks), static_cast<unsigned>(gy));
-        exact_scan_kernel<<<eg, 256, qsmem, st>>>(ep);
+        { ProfScope _ps(PROF_EXACT, st);
+        exact_scan_kernel<<<eg, 256, qsmem, st>>>(ep); }
         count_launch();
         RMU_CHECK_LAUNCH();
         FinalizeParams fp{};
@@ -1029,7 +1062,8 @@ int rmu_index_search(rmu_index* idx, const float* queries, int nq, int k, int64_
         fp.qmap = ep.qmap; fp.nsel = ep.nsel; fp.exact = 1;
         fp.k = k; fp.id_offset = id_offset; fp.max_norm_bits = idx->max_norm_bits; fp.eps_rel = 0.f;
         fp.out_scores = out_scores; fp.out_ids = reinterpret_cast<long long*>(out_ids); fp.flags = nullptr;
-        finalize_kernel<<<nq, 256, qsmem, st>>>(fp);
+        { ProfScope _ps(PROF_EXACT, st);
+        finalize_kernel<<<nq, 256, qsmem, st>>>(fp); }
         count_launch();
         RMU_CHECK_LAUNCH();
     }
@@ -1057,8 +1091,9 @@ int rmu_debug_scan_tile(rmu_index* idx, const float* queries, int nq, float* out
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     int rc = ensure_ws(idx, sizeof(unsigned long long) * kScanQ * 2 * 64 + 1024);
     if (rc != RMU_OK) return rc;
-    rc = make_tmap_2d(&idx->tmap, idx->x, static_cast<uint64_t>(idx->n), static_cast<uint64_t>(idx->dim),
-                      static_cast<uint64_t>(idx->dim) * sizeof(float), 32, scan_bn(), 4);
+    if (scan_kd() > 1) rc = make_tmap_rows_kblocks(&idx->tmap, idx->x, static_cast<uint64_t>(idx->n), idx->dim / 32, scan_bn(), scan_kd());
+    else rc = make_tmap_2d(&idx->tmap, idx->x, static_cast<uint64_t>(idx->n), static_cast<uint64_t>(idx->dim),
+                           static_cast<uint64_t>(idx->dim) * sizeof(float), 32, scan_bn(), 4);
     if (rc != RMU_OK) return rc;
     idx->tmap_rows = idx->n;
     idx->tmap_bn = scan_bn();
@@ -1117,6 +1152,7 @@ int rmu_topk_merge(const float* scores, const int64_t* ids, int R, int nq, int k
         RMU_CUDA(cudaFuncSetAttribute(merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
         attr_set = true;
     }
+    ProfScope _ps(PROF_MERGE, static_cast<cudaStream_t>(stream));
     merge_kernel<<<nq, 256, smem, static_cast<cudaStream_t>(stream)>>>(scores, reinterpret_cast<const long long*>(ids), R, nq, k,
                                                                        metric, out_scores, reinterpret_cast<long long*>(out_ids));
     count_launch();

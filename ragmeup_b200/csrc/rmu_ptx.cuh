@@ -76,6 +76,16 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const void* tmap, in
         "l"(policy)
         : "memory");
 }
+// 3-D tiled tensor load
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const void* tmap, int c0, int c1, int c2, uint64_t* bar,
+                                            uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+        " [%0], [%1, {%2, %3, %4}], [%5], %6;"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(c2),
+        "r"(smem_u32(bar)), "l"(policy)
+        : "memory");
+}
 // 1-D bulk copy global -> smem (size multiple of 16, both 16-B aligned)
 __device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
     asm volatile(

@@ -64,7 +64,7 @@ PRESETS: Dict[str, Tuple[BertConfig, str, int]] = {
     "bge-base-en-v1.5": (BertConfig(hidden=768, layers=12, heads=12, ffn=3072), "cls", 512),
     "GIST-small-Embedding-v0": (BertConfig(hidden=384, layers=12, heads=12, ffn=1536), "cls", 512),
     # tiny shapes for unit tests
-    "tiny": (BertConfig(vocab_size=1000, hidden=64, layers=2, heads=2, ffn=128, max_pos=128), "mean", 64),
+    "tiny": (BertConfig(vocab_size=1000, hidden=128, layers=2, heads=4, ffn=256, max_pos=128), "mean", 64),
 }
 
 

@@ -1,0 +1,189 @@
+"""GPU parity: flat index (tcgen05 scan + exact path + merge + MMR) vs the oracle and the goldens.
+ids: identical; scores: |d| <= 1e-3 (BASELINE.json), in practice ~1e-6."""
+import numpy as np
+import pytest
+import torch
+
+from cases import FLAT_CASES, flat_case
+from oracle import flat_ref
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-3
+
+
+def _idx(cuda, x, metric):
+    from ragmeup_b200.index import FlatIndex
+    ix = FlatIndex(x.shape[1], metric)
+    ix.add(x if isinstance(x, torch.Tensor) else np.ascontiguousarray(x))
+    return ix
+
+
+def _check(s, i, rs, ri):
+    i = i.cpu().numpy() if isinstance(i, torch.Tensor) else i
+    s = s.cpu().numpy() if isinstance(s, torch.Tensor) else s
+    assert (i == ri).all()
+    valid = ri >= 0
+    assert np.abs(s[valid] - rs[valid]).max() <= TOL
+    assert np.isinf(s[~valid]).all()
+
+
+@pytest.mark.parametrize("name", sorted(FLAT_CASES))
+@pytest.mark.parametrize("metric", ["ip", "cosine", "l2"])
+def test_golden_cases(cuda, golden_dir, name, metric):
+    """planted duplicates / ties, k > N, N = 1, D = 768, N big enough for the tensor scan (case e)"""
+    g = np.load(f"{golden_dir}/flat.npz")
+    x, q, k = flat_case(name)
+    ix = _idx(cuda, x, metric)
+    s, i = ix.search(torch.from_numpy(q).cuda(), k)
+    gi, gs = g[f"flat_{name}_{metric}_ids"], g[f"flat_{name}_{metric}_scores"]
+    i = i.cpu().numpy()
+    for r in range(q.shape[0]):                       # identical sets (golden order is fp64)
+        assert set(i[r].tolist()) == set(gi[r].tolist())
+    rs, ri = flat_ref.flat_search(q, x, k, metric)
+    _check(s, i, rs, ri)                              # identical order vs the fp32 oracle incl. the tie rule
+
+
+@pytest.mark.parametrize("metric", ["ip", "cosine", "l2"])
+@pytest.mark.parametrize("n,nq,k", [(16384, 3, 10), (50_001, 130, 20), (40_000, 1, 100), (30_000, 64, 50)])
+def test_tensor_scan_equals_exact_and_oracle(cuda, metric, n, nq, k):
+    from ragmeup_b200.index import MODE_AUTO, MODE_EXACT
+    g = torch.Generator(device="cuda").manual_seed(n + nq)
+    x = torch.randn(n, 384, device="cuda", generator=g)
+    if metric != "l2":
+        x = torch.nn.functional.normalize(x, dim=1)
+    x[n // 2] = x[7]                                  # duplicate rows -> tie decided by the lower row
+    q = torch.randn(nq, 384, device="cuda", generator=g)
+    q[0] = x[7]
+    ix = _idx(cuda, x, metric)
+    s0, i0 = ix.search(q, k, mode=MODE_EXACT)
+    s1, i1 = ix.search(q, k, mode=MODE_AUTO, want_stats=True)
+    assert ix.last_stats[1] >= 1                      # the tcgen05 scan ran
+    assert (i0 == i1).all() and (s0 == s1).all()      # bit-identical to the exact path
+    rs, ri = flat_ref.flat_search(q.cpu().numpy(), x.cpu().numpy(), k, metric)
+    _check(s1, i1, rs, ri)
+
+
+def test_certificate_falls_back_on_near_duplicates(cuda):
+    """more near-ties than the coarse pass keeps: the certificate must fail and the exact path answer"""
+    from ragmeup_b200.index import MODE_AUTO, MODE_TENSOR_NOFALLBACK
+    g = torch.Generator(device="cuda").manual_seed(3)
+    base = torch.nn.functional.normalize(torch.randn(1, 384, device="cuda", generator=g), dim=1)
+    x = torch.nn.functional.normalize(torch.randn(20000, 384, device="cuda", generator=g), dim=1)
+    x[1000:1400] = torch.nn.functional.normalize(base + 1e-4 * torch.randn(400, 384, device="cuda", generator=g), dim=1)
+    ix = _idx(cuda, x, "ip")
+    s, i = ix.search(base, 10, mode=MODE_AUTO, want_stats=True)
+    flagged = ix.last_stats[0]
+    rs, ri = flat_ref.flat_search(base.cpu().numpy(), x.cpu().numpy(), 10, "ip")
+    assert flagged == 1
+    _check(s, i, rs, ri)
+    ix.search(base, 10, mode=MODE_TENSOR_NOFALLBACK, want_stats=True)
+    assert ix.last_stats[0] == 1
+
+
+def test_empty_add_growth_offsets_and_host_api(cuda):
+    from ragmeup_b200.index import FlatIndex
+    ix = FlatIndex(64, "l2")
+    q = torch.randn(2, 64, device="cuda")
+    s, i = ix.search(q, 3)
+    assert (i == -1).all() and torch.isinf(s).all()
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal((2500, 64)).astype(np.float32)
+    for a in range(0, 2500, 700):                     # repeated adds force re-allocation
+        ix.add(x[a:a + 700])
+    assert len(ix) == 2500
+    s, i = ix.search(q, 5, id_offset=1000)
+    rs, ri = flat_ref.flat_search(q.cpu().numpy(), x, 5, "l2", id_offset=1000)
+    _check(s, i, rs, ri)
+    hs, hi = ix.search_host(q.cpu().numpy(), 5, id_offset=1000)
+    _check(hs, hi, rs, ri)
+    assert np.array_equal(ix.data().cpu().numpy(), x)
+    got = ix.gather(torch.tensor([3, 2499, 0], device="cuda")).cpu().numpy()
+    assert np.array_equal(got, x[[3, 2499, 0]])
+    ix.clear()
+    assert len(ix) == 0
+
+
+def test_dim_not_multiple_of_four_uses_exact_path(cuda):
+    rng = np.random.default_rng(1)
+    x = rng.standard_normal((20000, 50)).astype(np.float32)
+    q = rng.standard_normal((3, 50)).astype(np.float32)
+    ix = _idx(cuda, x, "cosine")
+    s, i = ix.search(torch.from_numpy(q).cuda(), 7, want_stats=True)
+    assert ix.last_stats[1] == 0
+    _check(s, i, *flat_ref.flat_search(q, x, 7, "cosine"))
+
+
+@pytest.mark.parametrize("R", [2, 4, 8])
+@pytest.mark.parametrize("metric", ["ip", "l2"])
+def test_shard_merge_kernel(cuda, R, metric):
+    """per-shard search + rmu_topk_merge == unsharded search == oracle (KA6)"""
+    from ragmeup_b200.index import topk_merge
+    g = torch.Generator(device="cuda").manual_seed(R)
+    n = 40_000
+    x = torch.nn.functional.normalize(torch.randn(n, 384, device="cuda", generator=g), dim=1)
+    x[n - 5] = x[11]                                  # duplicate in another shard
+    q = torch.nn.functional.normalize(torch.randn(9, 384, device="cuda", generator=g), dim=1)
+    q[0] = x[11]
+    k = 10
+    full = _idx(cuda, x, metric)
+    fs, fi = full.search(q, k)
+    bounds = [n * r // R for r in range(R + 1)]
+    ss, ii = [], []
+    for r in range(R):
+        sh = _idx(cuda, x[bounds[r]:bounds[r + 1]], metric)
+        s, i = sh.search(q, k, id_offset=bounds[r])
+        ss.append(s)
+        ii.append(i)
+    ms, mi = topk_merge(torch.stack(ss), torch.stack(ii), metric)
+    assert (mi == fi).all() and (ms == fs).all()
+    os_, oi = flat_ref.shard_merge(torch.stack(ss).cpu().numpy(), torch.stack(ii).cpu().numpy(), metric)
+    assert (mi.cpu().numpy() == oi).all()
+
+
+def test_mmr_matches_oracle(cuda):
+    from ragmeup_b200.index import mmr_select
+    g = torch.Generator(device="cuda").manual_seed(5)
+    q = torch.randn(6, 384, device="cuda", generator=g)
+    cand = torch.randn(6, 20, 384, device="cuda", generator=g) + q[:, None, :] * 0.7
+    cand[0, 3] = cand[0, 1]                           # duplicate candidate
+    n_cand = torch.tensor([20, 20, 20, 7, 1, 20], dtype=torch.int32)
+    sel = mmr_select(q, cand, n_cand, 10, 0.5).cpu().numpy()
+    for b in range(6):
+        n = int(n_cand[b])
+        want = flat_ref.mmr(q[b].cpu().numpy(), cand[b, :n].cpu().numpy(), 0.5, 10)
+        assert sel[b, :len(want)].tolist() == want
+        assert (sel[b, len(want):] == -1).all()
+    for lam in (0.0, 1.0, 0.3):
+        sel = mmr_select(q, cand, None, 4, lam).cpu().numpy()
+        for b in range(6):
+            assert sel[b].tolist() == flat_ref.mmr(q[b].cpu().numpy(), cand[b].cpu().numpy(), lam, 4)
+
+
+def test_large_corpus_properties(cuda):
+    """BASELINE size class (1M x 384, Q=64): planted neighbours must come back first; results are
+    sorted; searching twice is idempotent; shard-merge of two halves equals the full search."""
+    from ragmeup_b200.index import FlatIndex, topk_merge
+    n, d, nq, k = 1_000_000, 384, 64, 10
+    g = torch.Generator(device="cuda").manual_seed(1234)
+    ix = FlatIndex(d, "cosine")
+    ix.reserve(n)
+    halves = [FlatIndex(d, "cosine"), FlatIndex(d, "cosine")]
+    planted = None
+    for c in range(4):
+        x = torch.nn.functional.normalize(torch.randn(n // 4, d, device="cuda", generator=g), dim=1)
+        if c == 2:
+            planted = x[1000:1000 + nq].clone()
+        ix.add(x)
+        halves[c // 2].add(x)
+    q = torch.nn.functional.normalize(planted + 0.05 * torch.randn(nq, d, device="cuda", generator=g), dim=1)
+    s, i = ix.search(q, k, want_stats=True)
+    assert ix.last_stats[1] >= 1
+    want0 = torch.arange(nq, device="cuda") + 2 * (n // 4) + 1000
+    assert (i[:, 0] == want0).all()
+    assert (s[:, :-1] >= s[:, 1:]).all()
+    s2, i2 = ix.search(q, k)
+    assert (i2 == i).all() and (s2 == s).all()
+    a = halves[0].search(q, k)
+    b = halves[1].search(q, k, id_offset=n // 2)
+    ms, mi = topk_merge(torch.stack([a[0], b[0]]), torch.stack([a[1], b[1]]), "cosine")
+    assert (mi == i).all() and (ms == s).all()
