@@ -48,6 +48,7 @@ PAIR_LEN = Q_TOK + D_TOK + 3                    # [CLS] q [SEP] d [SEP] = 147
 DOC_TABLE = 65536                               # distinct synthetic documents' token rows
 CHUNK = 250_000                                 # corpus generation granularity (seed per global chunk)
 METRIC = os.environ.get("BENCH_METRIC", "cosine")
+CE_CHUNK = int(os.environ.get("BENCH_CE_CHUNK", 400))      # rerank pairs per encoder call (58.8k tokens)
 
 
 def peaks():
@@ -175,8 +176,12 @@ def run_gpu(args):
         _, ids = sh.search(q_emb, R)                                   # [Q, R] global ids, best first
         docs = doc_tab[(ids % DOC_TABLE)]                              # [Q, R, D_TOK]
         pairs = torch.cat([cls_col, q_tok[:, None, :].expand(Q, R, Q_TOK), sep_col, docs, sep_col], 2)
-        mine = pairs.reshape(npairs, PAIR_LEN)[p0:p1].reshape(-1)
-        logits = ce.classify_tokens(mine, pair_typ, pair_cu, PAIR_LEN)[:, 0]
+        mine = pairs.reshape(npairs, PAIR_LEN)[p0:p1]
+        outs = []
+        for c0_ in range(0, p1 - p0, CE_CHUNK):               # bounded activation workspace per call
+            n_ = min(CE_CHUNK, p1 - p0 - c0_)
+            outs.append(ce.classify_tokens(mine[c0_:c0_ + n_].reshape(-1), pair_typ[: n_ * PAIR_LEN], pair_cu[: n_ + 1], PAIR_LEN)[:, 0])
+        logits = outs[0] if len(outs) == 1 else torch.cat(outs)
         if world > 1:
             parts = [torch.empty_like(logits) for _ in range(world)]
             dist.all_gather(parts, logits)

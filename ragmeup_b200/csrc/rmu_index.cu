@@ -186,11 +186,17 @@ struct ScanParams {
     unsigned long long* lists;  // [gridDim.x][128][2*KEEP]
     float* dbg;            // diagnostics: CTA 0 dumps the raw accumulators of its first tile [128][BN]
     int ablate;            // profiling only: bit0 skip MMA issue, bit1 skip epilogue work, bit2 skip TMEM loads
+    // threshold exchange: phase 0 = whole range in one launch; phase 1 = only the first `lead` tiles of
+    // every CTA (leaves sorted lists + counts); phase 2 = the rest, starting from the lists of phase 1 and
+    // the per-query global threshold tau0 (KEEP-th best key over ALL CTAs' phase-1 lists).
+    int phase, lead;
+    const float* tau0;     // [nq_total]
+    int* counts;           // [gridDim.x][128]
 };
 
 // BN rows per tile (= MMA N), NBUF TMEM accumulators, NSLAB pipeline stages, each stage = KD K-blocks
 // (one TMA op; KD > 1 uses the 3-D (32, rows, kblock) tensor map and needs dim % 32 == 0)
-template <int BN, int NBUF, int NSLAB, int KD, int KEEP>
+template <int BN, int NBUF, int NSLAB, int KD, bool TMA3D, int KEEP>
 __global__ void __launch_bounds__(kScanThreads, 1)
 scan_tf32_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
     constexpr int CAP = 2 * KEEP;
@@ -225,8 +231,10 @@ scan_tf32_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
     const uint32_t tmem_base = *tmem_slot;
 
     // contiguous tile range of this CTA
-    const int t0 = static_cast<int>((static_cast<long long>(blockIdx.x) * p.ntiles) / gridDim.x);
-    const int t1 = static_cast<int>((static_cast<long long>(blockIdx.x + 1) * p.ntiles) / gridDim.x);
+    int t0 = static_cast<int>((static_cast<long long>(blockIdx.x) * p.ntiles) / gridDim.x);
+    int t1 = static_cast<int>((static_cast<long long>(blockIdx.x + 1) * p.ntiles) / gridDim.x);
+    if (p.phase == 1) t1 = min(t1, t0 + p.lead);
+    if (p.phase == 2) t0 = min(t1, t0 + p.lead);
 
     // ---- query block -> TMEM (A operand): lane = query, column = dimension, zero padded
     const int quad = warp & 3;  // TMEM lane quadrant this warp may touch
@@ -257,8 +265,16 @@ scan_tf32_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
                 for (int kb = 0; kb < KB; kb += KD) {
                     mbar_wait(&empty[slot], phase ^ 1);
                     mbar_arrive_expect_tx(&full[slot], SLAB_BYTES);
-                    if (KD == 1) tma_load_2d(slabs + slot * SLAB_BYTES, &tmap, kb * 32, t * BN, &full[slot], kEvictFirst);
-                    else tma_load_3d(slabs + slot * SLAB_BYTES, &tmap, 0, t * BN, kb, &full[slot], kEvictFirst);
+                    if (TMA3D) {
+                        tma_load_3d(slabs + slot * SLAB_BYTES, &tmap, 0, t * BN, kb, &full[slot], kEvictFirst);
+                    } else {
+                        // KD boxes of {128 B, BN rows} credited to one barrier (K-blocks past the row end are
+                        // out of bounds and arrive as zeros, still counting their bytes)
+#pragma unroll
+                        for (int kk = 0; kk < KD; ++kk)
+                            tma_load_2d(slabs + slot * SLAB_BYTES + kk * (BN * 128), &tmap, (kb + kk) * 32, t * BN,
+                                        &full[slot], kEvictFirst);
+                    }
                     if (++slot == NSLAB) { slot = 0; phase ^= 1; }
                 }
             }
@@ -304,6 +320,11 @@ scan_tf32_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
         unsigned long long* mybuf = p.lists + (static_cast<long long>(blockIdx.x) * kScanQ + qi) * CAP;
         int cnt = 0;
         float tau = live ? -INFINITY : INFINITY;
+        if (p.phase == 2 && live) {
+            cnt = p.counts[blockIdx.x * kScanQ + qi];
+            if (cnt >= KEEP) tau = key_score(mybuf[KEEP - 1]);
+            tau = fmaxf(tau, p.tau0[p.q0 + qi]);
+        }
         const bool has_sb = (p.rscale != nullptr) || (p.rbias != nullptr);
         for (int t = t0; t < t1; ++t) {
             const int i = t - t0;
@@ -369,6 +390,7 @@ scan_tf32_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
         // final: every list sorted descending, zero padded to KEEP entries
         warp_compact<KEEP>(mybuf, cnt, tau, true);
         for (int e = cnt; e < KEEP; ++e) mybuf[e] = 0ull;
+        if (p.phase == 1) p.counts[blockIdx.x * kScanQ + qi] = cnt;
     }
 
     tc_fence_before();
@@ -440,6 +462,62 @@ __global__ void __launch_bounds__(256) exact_scan_kernel(const ExactParams p) {
     }
 }
 
+// Block-wide radix select (8 bits per pass, most significant first): returns the ksel-th largest non-zero
+// key among load_key(0..total), or 1 ("keep everything") when fewer than ksel exist.  All threads call.
+template <typename LoadKey>
+__device__ __forceinline__ unsigned long long block_radix_select(LoadKey load_key, long long total, int ksel, int* hist,
+                                                                 unsigned long long* s_prefix, int* s_remaining) {
+    const int tid = threadIdx.x;
+    if (tid == 0) { *s_prefix = 0ull; *s_remaining = ksel; }
+    __syncthreads();
+    for (int pass = 0; pass < 8; ++pass) {
+        const int shift = 56 - 8 * pass;
+        for (int i = tid; i < 256; i += blockDim.x) hist[i] = 0;
+        __syncthreads();
+        const unsigned long long prefix = *s_prefix;
+        const int remaining = *s_remaining;         // < 0: fewer than ksel keys exist, keep all
+        const unsigned long long himask = pass == 0 ? 0ull : (~0ull << (shift + 8));
+        if (remaining >= 0) {
+            for (long long idx = tid; idx < total; idx += blockDim.x) {
+                const unsigned long long key = load_key(idx);
+                if (key != 0ull && (key & himask) == prefix) atomicAdd(&hist[(key >> shift) & 0xFF], 1);
+            }
+        }
+        __syncthreads();
+        if (tid == 0 && remaining >= 0) {
+            int rem = remaining;
+            int b = 255;
+            for (; b >= 0; --b) {
+                if (hist[b] >= rem) break;
+                rem -= hist[b];
+            }
+            if (b < 0) { *s_remaining = -1; }
+            else { *s_prefix = prefix | (static_cast<unsigned long long>(b) << shift); *s_remaining = rem; }
+        }
+        __syncthreads();
+    }
+    return *s_remaining < 0 ? 1ull : *s_prefix;
+}
+
+// per-query global threshold for phase 2 of the scan: score of the keep-th best key over all CTAs'
+// phase-1 lists (-inf when fewer than keep candidates exist yet)
+__global__ void __launch_bounds__(256) select_tau_kernel(const unsigned long long* __restrict__ lists, int nlists, int lstride,
+                                                         int len, int keep, int q0, float* __restrict__ tau0) {
+    __shared__ int hist[256];
+    __shared__ unsigned long long s_prefix;
+    __shared__ int s_remaining;
+    const int f = blockIdx.x;
+    const long long total = static_cast<long long>(nlists) * len;
+    const int len_shift = __ffs(len) - 1;
+    auto load_key = [&](long long idx) -> unsigned long long {
+        const long long l = idx >> len_shift;
+        const int e = static_cast<int>(idx & (len - 1));
+        return lists[(l * kScanQ + f) * lstride + e];
+    };
+    const unsigned long long T = block_radix_select(load_key, total, keep, hist, &s_prefix, &s_remaining);
+    if (threadIdx.x == 0) tau0[q0 + f] = (T <= 1ull) ? -INFINITY : key_score(T);
+}
+
 // =====================================================================================================
 // (2) finalize: global selection of the best KSEL candidates, exact re-score, sort, certificate
 // =====================================================================================================
@@ -496,36 +574,9 @@ __global__ void __launch_bounds__(256) finalize_kernel(const FinalizeParams p) {
         return p.lists[(l * p.qstride + qslot) * p.lstride + e];
     };
 
-    // ---- radix select (8 bits per pass, most significant first) of the ksel-th largest key
-    if (tid == 0) { s_prefix = 0ull; s_remaining = p.ksel; s_ncand = 0; }
+    const unsigned long long T = block_radix_select(load_key, total, p.ksel, hist, &s_prefix, &s_remaining);
+    if (tid == 0) s_ncand = 0;
     __syncthreads();
-    for (int pass = 0; pass < 8; ++pass) {
-        const int shift = 56 - 8 * pass;
-        for (int i = tid; i < 256; i += blockDim.x) hist[i] = 0;
-        __syncthreads();
-        const unsigned long long prefix = s_prefix;
-        const int remaining = s_remaining;          // < 0: fewer than ksel keys exist, keep all
-        const unsigned long long himask = pass == 0 ? 0ull : (~0ull << (shift + 8));
-        if (remaining >= 0) {
-            for (long long idx = tid; idx < total; idx += blockDim.x) {
-                const unsigned long long key = load_key(idx);
-                if (key != 0ull && (key & himask) == prefix) atomicAdd(&hist[(key >> shift) & 0xFF], 1);
-            }
-        }
-        __syncthreads();
-        if (tid == 0 && remaining >= 0) {
-            int rem = remaining;
-            int b = 255;
-            for (; b >= 0; --b) {
-                if (hist[b] >= rem) break;
-                rem -= hist[b];
-            }
-            if (b < 0) { s_remaining = -1; }
-            else { s_prefix = prefix | (static_cast<unsigned long long>(b) << shift); s_remaining = rem; }
-        }
-        __syncthreads();
-    }
-    const unsigned long long T = s_remaining < 0 ? 1ull : s_prefix;  // ksel-th largest key, or "all"
     // ---- collect keys >= T
     long long nonzero_local = 0;
     for (long long idx = tid; idx < total; idx += blockDim.x) {
@@ -807,9 +858,9 @@ static int keep_for_k(int k) {
     return 256;
 }
 
-template <int BN, int NBUF, int NSLAB, int KD, int KEEP>
+template <int BN, int NBUF, int NSLAB, int KD, bool TMA3D, int KEEP>
 static int launch_scan(const CUtensorMap& tmap, const ScanParams& p, int grid, cudaStream_t st) {
-    auto kern = scan_tf32_kernel<BN, NBUF, NSLAB, KD, KEEP>;
+    auto kern = scan_tf32_kernel<BN, NBUF, NSLAB, KD, TMA3D, KEEP>;
     const size_t smem = static_cast<size_t>(NSLAB) * BN * 128 * KD + 32 * 128 * sizeof(float) + (2 * NSLAB + 2 * NBUF) * 8 + 16 + 1024;
     static bool attr_set = false;
     if (!attr_set) {
@@ -823,30 +874,34 @@ static int launch_scan(const CUtensorMap& tmap, const ScanParams& p, int grid, c
     return RMU_OK;
 }
 
-// scan geometry variants {rows per tile, TMEM accumulators, stages, K-blocks per TMA op}:
-//   0: 64 x 2, 24 x  8 KB (2-D map)      1: 128 x 1, 12 x 16 KB (2-D map)
-//   2: 64 x 2,  6 x 32 KB (3-D map, 4 K-blocks per op)   3: 64 x 2, 12 x 16 KB (3-D, 2 per op)
-//   4: 64 x 2,  4 x 48 KB (3-D, 6 per op)
+// scan geometry variants {rows per tile, TMEM accumulators, stages, K-blocks per stage, 3-D map}:
+//   0: 64 x 2, 24 x  8 KB (2-D)           1: 128 x 1, 12 x 16 KB (2-D)
+//   2: 64 x 2,  6 x 32 KB (3-D, 4 kb/op)  3: 64 x 2, 12 x 16 KB (3-D, 2 kb/op)   4: 64 x 2, 4 x 48 KB (3-D, 6 kb/op)
+//   5: 128 x 1, 4 stages x 3 boxes of 16 KB   6: 128 x 1, 3 stages x 4 boxes   7: 128 x 1, 2 stages x 6 boxes
 static int scan_variant() {
     static int v = -1;
     if (v < 0) {
         const char* e = getenv("RMU_SCAN_VARIANT");
-        v = e ? atoi(e) : 1;
-        if (v < 0 || v > 4) v = 1;
+        v = e ? atoi(e) : 5;
+        if (v < 0 || v > 7) v = 5;
     }
     return v;
 }
-static int scan_bn() { return scan_variant() == 1 ? 128 : 64; }
-static int scan_kd() { const int v = scan_variant(); return v == 2 ? 4 : v == 3 ? 2 : v == 4 ? 6 : 1; }
+static bool scan_3d() { const int v = scan_variant(); return v >= 2 && v <= 4; }
+static int scan_bn() { const int v = scan_variant(); return (v == 1 || v >= 5) ? 128 : 64; }
+static int scan_kd() { const int v = scan_variant(); return v == 2 ? 4 : v == 3 ? 2 : v == 4 ? 6 : 1; }   // 3-D box depth
 
 template <int KEEP>
 static int dispatch_variant(const CUtensorMap& tmap, const ScanParams& p, int grid, cudaStream_t st) {
     switch (scan_variant()) {
-        case 1: return launch_scan<128, 1, 12, 1, KEEP>(tmap, p, grid, st);
-        case 2: return launch_scan<64, 2, 6, 4, KEEP>(tmap, p, grid, st);
-        case 3: return launch_scan<64, 2, 12, 2, KEEP>(tmap, p, grid, st);
-        case 4: return launch_scan<64, 2, 4, 6, KEEP>(tmap, p, grid, st);
-        default: return launch_scan<64, 2, 24, 1, KEEP>(tmap, p, grid, st);
+        case 0: return launch_scan<64, 2, 24, 1, false, KEEP>(tmap, p, grid, st);
+        case 1: return launch_scan<128, 1, 12, 1, false, KEEP>(tmap, p, grid, st);
+        case 2: return launch_scan<64, 2, 6, 4, true, KEEP>(tmap, p, grid, st);
+        case 3: return launch_scan<64, 2, 12, 2, true, KEEP>(tmap, p, grid, st);
+        case 4: return launch_scan<64, 2, 4, 6, true, KEEP>(tmap, p, grid, st);
+        case 6: return launch_scan<128, 1, 3, 4, false, KEEP>(tmap, p, grid, st);
+        case 7: return launch_scan<128, 1, 2, 6, false, KEEP>(tmap, p, grid, st);
+        default: return launch_scan<128, 1, 4, 3, false, KEEP>(tmap, p, grid, st);
     }
 }
 
@@ -976,6 +1031,8 @@ int rmu_index_search(rmu_index* idx, const float* queries, int nq, int k, int64_
     const size_t o_qmap = carve(sizeof(int) * nq);
     const size_t o_nsel = carve(sizeof(int) * 4);
     const size_t o_scan = tensor_ok ? carve(sizeof(unsigned long long) * grid_scan * kScanQ * 2 * keep) : 0;
+    const size_t o_tau = carve(sizeof(float) * nq);
+    const size_t o_cnt = carve(sizeof(int) * grid_scan * kScanQ);
     const size_t o_exact = carve(sizeof(unsigned long long) * std::max(nchunks, 1) * static_cast<size_t>(nq) * keepx);
     int rc = ensure_ws(idx, off);
     if (rc != RMU_OK) return rc;
@@ -985,6 +1042,8 @@ int rmu_index_search(rmu_index* idx, const float* queries, int nq, int k, int64_
     int* d_nsel = reinterpret_cast<int*>(ws + o_nsel);
     unsigned long long* d_scan = reinterpret_cast<unsigned long long*>(ws + o_scan);
     unsigned long long* d_exact = reinterpret_cast<unsigned long long*>(ws + o_exact);
+    float* d_tau0 = reinterpret_cast<float*>(ws + o_tau);
+    int* d_cnt = reinterpret_cast<int*>(ws + o_cnt);
 
     const size_t qsmem = static_cast<size_t>(D) * sizeof(float);
     int scan_launches = 0;
@@ -1005,7 +1064,7 @@ int rmu_index_search(rmu_index* idx, const float* queries, int nq, int k, int64_
 
     if (tensor_ok) {
         if (idx->tmap_rows != N || idx->tmap_bn != scan_bn()) {
-            if (scan_kd() > 1) {
+            if (scan_3d()) {
                 if (D % 32 != 0) { set_error("scan variant needs dim % 32 == 0"); return RMU_ERR_UNSUPPORTED; }
                 rc = make_tmap_rows_kblocks(&idx->tmap, idx->x, static_cast<uint64_t>(N), D / 32, scan_bn(), scan_kd());
             } else {
@@ -1025,9 +1084,31 @@ int rmu_index_search(rmu_index* idx, const float* queries, int nq, int k, int64_
             sp.lists = d_scan;
             { static const char* ab = getenv("RMU_SCAN_ABLATE"); sp.ablate = ab ? atoi(ab) : 0; }
             const int grid = std::min(grid_scan, ntiles);
-            rc = dispatch_scan(keep, idx->tmap, sp, grid, st);
-            if (rc != RMU_OK) return rc;
-            ++scan_launches;
+            // threshold exchange (big corpora): every CTA first scans a lead of its range, the per-query
+            // KEEP-th best over all CTAs becomes the starting threshold of the main pass
+            static const int lead_pct = [] { const char* e = getenv("RMU_SCAN_LEAD_PCT"); return e ? atoi(e) : 6; }();
+            const int tiles_per_cta = ntiles / grid;
+            const bool exchange = lead_pct > 0 && tiles_per_cta >= 16;
+            sp.tau0 = d_tau0; sp.counts = d_cnt;
+            if (exchange) {
+                sp.phase = 1;
+                sp.lead = std::max(2, (tiles_per_cta * lead_pct + 99) / 100);
+                rc = dispatch_scan(keep, idx->tmap, sp, grid, st);
+                if (rc != RMU_OK) return rc;
+                { ProfScope _ps(PROF_FINALIZE, st);
+                select_tau_kernel<<<sp.nq, 256, 0, st>>>(d_scan, grid, 2 * keep, keep, keep, q0, d_tau0); }
+                count_launch();
+                RMU_CHECK_LAUNCH();
+                sp.phase = 2;
+                rc = dispatch_scan(keep, idx->tmap, sp, grid, st);
+                if (rc != RMU_OK) return rc;
+                scan_launches += 2;
+            } else {
+                sp.phase = 0;
+                rc = dispatch_scan(keep, idx->tmap, sp, grid, st);
+                if (rc != RMU_OK) return rc;
+                ++scan_launches;
+            }
             FinalizeParams fp{};
             fp.lists = d_scan; fp.nlists = grid; fp.qstride = kScanQ; fp.lstride = 2 * keep; fp.len = keep; fp.ksel = keep;
             fp.x = idx->x; fp.n = N; fp.dim = D; fp.metric = idx->metric; fp.q = queries; fp.q0 = q0; fp.exact = 0;
@@ -1091,7 +1172,7 @@ int rmu_debug_scan_tile(rmu_index* idx, const float* queries, int nq, float* out
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     int rc = ensure_ws(idx, sizeof(unsigned long long) * kScanQ * 2 * 64 + 1024);
     if (rc != RMU_OK) return rc;
-    if (scan_kd() > 1) rc = make_tmap_rows_kblocks(&idx->tmap, idx->x, static_cast<uint64_t>(idx->n), idx->dim / 32, scan_bn(), scan_kd());
+    if (scan_3d()) rc = make_tmap_rows_kblocks(&idx->tmap, idx->x, static_cast<uint64_t>(idx->n), idx->dim / 32, scan_bn(), scan_kd());
     else rc = make_tmap_2d(&idx->tmap, idx->x, static_cast<uint64_t>(idx->n), static_cast<uint64_t>(idx->dim),
                            static_cast<uint64_t>(idx->dim) * sizeof(float), 32, scan_bn(), 4);
     if (rc != RMU_OK) return rc;

@@ -27,6 +27,26 @@ def _check(s, i, rs, ri):
     assert np.isinf(s[~valid]).all()
 
 
+def _check_topk_fp64(s, i, q, x, k, metric):
+    """ids identical to an exact search up to fp32 near-ties: judged in float64 — returned scores
+    within TOL, returned order sorted, and no excluded row better than the k-th returned one, with a
+    slack of a few fp32 ulps of the score magnitude (unnormalised L2 distances are ~1e3, so two
+    fp32 implementations may order rows whose distances differ by < 1e-4 either way)."""
+    i = i.cpu().numpy()
+    s = s.cpu().numpy().astype(np.float64)
+    v = flat_ref.metric_values(q, x, metric, dtype=np.float64)
+    rank = v if metric == "l2" else -v
+    eps = 8 * np.finfo(np.float32).eps * max(1.0, float(np.abs(v).max()))
+    for r in range(q.shape[0]):
+        ids = i[r]
+        assert (ids >= 0).all() and len(set(ids.tolist())) == len(ids)
+        got = rank[r, ids]
+        assert np.abs(s[r] - v[r, ids]).max() <= TOL * max(1.0, float(np.abs(v[r, ids]).max()) * 1e-2)
+        assert (got[:-1] <= got[1:] + eps).all()
+        rest = np.delete(rank[r], ids)
+        assert rest.min() >= got[-1] - eps
+
+
 @pytest.mark.parametrize("name", sorted(FLAT_CASES))
 @pytest.mark.parametrize("metric", ["ip", "cosine", "l2"])
 def test_golden_cases(cuda, golden_dir, name, metric):
@@ -59,23 +79,28 @@ def test_tensor_scan_equals_exact_and_oracle(cuda, metric, n, nq, k):
     s1, i1 = ix.search(q, k, mode=MODE_AUTO, want_stats=True)
     assert ix.last_stats[1] >= 1                      # the tcgen05 scan ran
     assert (i0 == i1).all() and (s0 == s1).all()      # bit-identical to the exact path
-    rs, ri = flat_ref.flat_search(q.cpu().numpy(), x.cpu().numpy(), k, metric)
-    _check(s1, i1, rs, ri)
+    if metric == "l2":
+        _check_topk_fp64(s1, i1, q.cpu().numpy(), x.cpu().numpy(), k, metric)
+    else:
+        rs, ri = flat_ref.flat_search(q.cpu().numpy(), x.cpu().numpy(), k, metric)
+        _check(s1, i1, rs, ri)
 
 
 def test_certificate_falls_back_on_near_duplicates(cuda):
-    """more near-ties than the coarse pass keeps: the certificate must fail and the exact path answer"""
-    from ragmeup_b200.index import MODE_AUTO, MODE_TENSOR_NOFALLBACK
+    """more near-ties than the coarse pass keeps: the certificate must fail and the exact fp32 scan must
+    answer (bit-identical to MODE_EXACT; valid top-k in float64 up to fp32 near-ties)"""
+    from ragmeup_b200.index import MODE_AUTO, MODE_EXACT, MODE_TENSOR_NOFALLBACK
     g = torch.Generator(device="cuda").manual_seed(3)
     base = torch.nn.functional.normalize(torch.randn(1, 384, device="cuda", generator=g), dim=1)
     x = torch.nn.functional.normalize(torch.randn(20000, 384, device="cuda", generator=g), dim=1)
     x[1000:1400] = torch.nn.functional.normalize(base + 1e-4 * torch.randn(400, 384, device="cuda", generator=g), dim=1)
     ix = _idx(cuda, x, "ip")
     s, i = ix.search(base, 10, mode=MODE_AUTO, want_stats=True)
-    flagged = ix.last_stats[0]
-    rs, ri = flat_ref.flat_search(base.cpu().numpy(), x.cpu().numpy(), 10, "ip")
-    assert flagged == 1
-    _check(s, i, rs, ri)
+    assert ix.last_stats[0] == 1                      # flagged -> re-run on the exact path
+    s0, i0 = ix.search(base, 10, mode=MODE_EXACT)
+    assert (i == i0).all() and (s == s0).all()
+    assert ((i >= 1000) & (i < 1400)).all()
+    _check_topk_fp64(s, i, base.cpu().numpy(), x.cpu().numpy(), 10, "ip")
     ix.search(base, 10, mode=MODE_TENSOR_NOFALLBACK, want_stats=True)
     assert ix.last_stats[0] == 1
 
