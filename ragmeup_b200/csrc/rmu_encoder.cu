@@ -12,6 +12,7 @@
 //
 // Activations between kernels are split fp16 planes (see rmu_gemm.cuh); LayerNorm, softmax, GELU,
 // residual adds, pooling and the classifier head are fp32.
+#include <algorithm>
 #include <cstdlib>
 #include <mutex>
 #include <vector>
@@ -33,7 +34,9 @@ __global__ void split_planes_kernel(const float* __restrict__ src, __half* __res
 
 constexpr int kMaxPerLane = 32;  // hidden <= 1024
 
-// LayerNorm of one row held as v[i] = x[lane + 32 i]; biased variance, eps inside the sqrt (nn.LayerNorm)
+// LayerNorm of one row.  Lane l holds the CONTIGUOUS elements x[l*per_lane .. +per_lane) (per_lane % 4 == 0),
+// so loads are float4 and the split planes are written 8 bytes at a time.  Biased variance, eps inside
+// the sqrt (nn.LayerNorm).
 __device__ __forceinline__ void warp_layernorm_store(float (&v)[kMaxPerLane], int per_lane, int H, float eps,
                                                      const float* __restrict__ g, const float* __restrict__ b,
                                                      __half* __restrict__ hi, __half* __restrict__ lo) {
@@ -48,15 +51,23 @@ __device__ __forceinline__ void warp_layernorm_store(float (&v)[kMaxPerLane], in
     for (int i = 0; i < kMaxPerLane; ++i) if (i < per_lane) { const float d = v[i] - mean; q = fmaf(d, d, q); }
     for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
     const float rstd = 1.0f / sqrtf(q / static_cast<float>(H) + eps);
+    const int d0 = lane * per_lane;
 #pragma unroll
-    for (int i = 0; i < kMaxPerLane; ++i) {
+    for (int i = 0; i < kMaxPerLane; i += 4) {
         if (i < per_lane) {
-            const int d = lane + 32 * i;
-            const float y = (v[i] - mean) * rstd * g[d] + b[d];
-            __half h, l;
-            split_f16(y, h, l);
-            hi[d] = h;
-            lo[d] = l;
+            const float4 gg = *reinterpret_cast<const float4*>(g + d0 + i);
+            const float4 bb = *reinterpret_cast<const float4*>(b + d0 + i);
+            const float y0 = (v[i] - mean) * rstd * gg.x + bb.x, y1 = (v[i + 1] - mean) * rstd * gg.y + bb.y;
+            const float y2 = (v[i + 2] - mean) * rstd * gg.z + bb.z, y3 = (v[i + 3] - mean) * rstd * gg.w + bb.w;
+            __half h0, l0, h1, l1, h2, l2, h3, l3;
+            split_f16(y0, h0, l0); split_f16(y1, h1, l1); split_f16(y2, h2, l2); split_f16(y3, h3, l3);
+            __half2 ha = __halves2half2(h0, h1), hb = __halves2half2(h2, h3);
+            __half2 la = __halves2half2(l0, l1), lb = __halves2half2(l2, l3);
+            uint2 ph, pl;
+            ph.x = *reinterpret_cast<uint32_t*>(&ha); ph.y = *reinterpret_cast<uint32_t*>(&hb);
+            pl.x = *reinterpret_cast<uint32_t*>(&la); pl.y = *reinterpret_cast<uint32_t*>(&lb);
+            *reinterpret_cast<uint2*>(hi + d0 + i) = ph;
+            *reinterpret_cast<uint2*>(lo + d0 + i) = pl;
         }
     }
 }
@@ -81,16 +92,20 @@ __global__ void embed_ln_kernel(const int* __restrict__ ids, const int* __restri
     id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
     int ty = type_ids ? type_ids[t] : 0;
     ty = ty < 0 ? 0 : (ty >= type_vocab ? type_vocab - 1 : ty);
-    const float* w = word + static_cast<size_t>(id) * H;
-    const float* pp = pos + static_cast<size_t>(p) * H;
-    const float* tt = typ + static_cast<size_t>(ty) * H;
     const int per_lane = H >> 5;
+    const int d0 = lane_id() * per_lane;
+    const float* w = word + static_cast<size_t>(id) * H + d0;
+    const float* pp = pos + static_cast<size_t>(p) * H + d0;
+    const float* tt = typ + static_cast<size_t>(ty) * H + d0;
     float v[kMaxPerLane];
 #pragma unroll
-    for (int i = 0; i < kMaxPerLane; ++i) {
+    for (int i = 0; i < kMaxPerLane; i += 4) {
         if (i < per_lane) {
-            const int d = lane_id() + 32 * i;
-            v[i] = (w[d] + tt[d]) + pp[d];   // HF: inputs_embeds + token_type_embeddings, then + position
+            const float4 a = *reinterpret_cast<const float4*>(w + i);
+            const float4 c = *reinterpret_cast<const float4*>(tt + i);
+            const float4 e = *reinterpret_cast<const float4*>(pp + i);
+            // HF: inputs_embeds + token_type_embeddings, then + position_embeddings
+            v[i] = (a.x + c.x) + e.x; v[i + 1] = (a.y + c.y) + e.y; v[i + 2] = (a.z + c.z) + e.z; v[i + 3] = (a.w + c.w) + e.w;
         }
     }
     warp_layernorm_store(v, per_lane, H, eps, g, b, hi + static_cast<size_t>(t) * H, lo + static_cast<size_t>(t) * H);
@@ -102,10 +117,15 @@ __global__ void ln_kernel(const float* __restrict__ pre, int T, int H, const flo
     const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (t >= T) return;
     const int per_lane = H >> 5;
-    const float* row = pre + static_cast<size_t>(t) * H;
+    const float* row = pre + static_cast<size_t>(t) * H + lane_id() * per_lane;
     float v[kMaxPerLane];
 #pragma unroll
-    for (int i = 0; i < kMaxPerLane; ++i) if (i < per_lane) v[i] = row[lane_id() + 32 * i];
+    for (int i = 0; i < kMaxPerLane; i += 4) {
+        if (i < per_lane) {
+            const float4 a = *reinterpret_cast<const float4*>(row + i);
+            v[i] = a.x; v[i + 1] = a.y; v[i + 2] = a.z; v[i + 3] = a.w;
+        }
+    }
     warp_layernorm_store(v, per_lane, H, eps, g, b, hi + static_cast<size_t>(t) * H, lo + static_cast<size_t>(t) * H);
 }
 
@@ -402,6 +422,211 @@ __global__ void __launch_bounds__(256) attention_mma_kernel(const float* __restr
     }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// attention_planes_kernel: same algorithm as attention_mma_kernel, but Q (pre-scaled), K and V arrive as
+// split fp16 planes [T, 3H] written by the QKV GEMM epilogue, so this kernel does no conversion work:
+// K / V tiles are 16-byte copies into shared memory ([key][d] for both) and the P V operand is fetched
+// with ldmatrix.trans.  One CTA = (sequence, head, block of 16*NW query rows), one warp = 16 rows.
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], const void* smem_row) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+                 : "r"(smem_u32(smem_row)));
+}
+
+constexpr int kAttWarps = 10;   // 160 query rows per CTA (a 147-token rerank pair fits one CTA)
+
+__device__ __forceinline__ float fast_exp2(float x) {   // ex2.approx: 2 ulp, exp2(-inf) = +0
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+template <int DH>
+__global__ void __launch_bounds__(kAttWarps * 32) attention_planes_kernel(const __half* __restrict__ ph, const __half* __restrict__ pl,
+                                                                          const int* __restrict__ cu, int H, int ksb,
+                                                                          __half* __restrict__ ctx_hi, __half* __restrict__ ctx_lo) {
+    constexpr int KSTR = DH + 8;
+    constexpr int KS = DH / 16;
+    constexpr int NT = DH / 8;
+    extern __shared__ __align__(16) unsigned char att_smem[];
+    __half* Kh = reinterpret_cast<__half*>(att_smem);
+    __half* Kl = Kh + ksb * KSTR;           // ksb = keys resident at a time (multiple of 32, <= kKeySB)
+    __half* Vh = Kl + ksb * KSTR;
+    __half* Vl = Vh + ksb * KSTR;
+
+    const int b = blockIdx.x, h = blockIdx.y;
+    const int t0 = cu[b], S = cu[b + 1] - t0;
+    const int rbase = blockIdx.z * (kAttWarps * 16);
+    if (rbase >= S) return;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    const size_t ld = static_cast<size_t>(3) * H;
+    const __half* qh_base = ph + static_cast<size_t>(t0) * ld + h * DH;
+    const __half* ql_base = pl + static_cast<size_t>(t0) * ld + h * DH;
+    const int r0 = rbase + warp * 16;
+    const bool warp_live = r0 < S;
+
+    uint32_t qh[KS][4], ql[KS][4];
+    {
+        const int ra = r0 + g, rb = r0 + g + 8;
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { qh[ks][i] = 0u; ql[ks][i] = 0u; }
+            if (warp_live && ra < S) {
+                qh[ks][0] = *reinterpret_cast<const uint32_t*>(qh_base + ra * ld + ks * 16 + 2 * t);
+                ql[ks][0] = *reinterpret_cast<const uint32_t*>(ql_base + ra * ld + ks * 16 + 2 * t);
+                qh[ks][2] = *reinterpret_cast<const uint32_t*>(qh_base + ra * ld + ks * 16 + 2 * t + 8);
+                ql[ks][2] = *reinterpret_cast<const uint32_t*>(ql_base + ra * ld + ks * 16 + 2 * t + 8);
+            }
+            if (warp_live && rb < S) {
+                qh[ks][1] = *reinterpret_cast<const uint32_t*>(qh_base + rb * ld + ks * 16 + 2 * t);
+                ql[ks][1] = *reinterpret_cast<const uint32_t*>(ql_base + rb * ld + ks * 16 + 2 * t);
+                qh[ks][3] = *reinterpret_cast<const uint32_t*>(qh_base + rb * ld + ks * 16 + 2 * t + 8);
+                ql[ks][3] = *reinterpret_cast<const uint32_t*>(ql_base + rb * ld + ks * 16 + 2 * t + 8);
+            }
+        }
+    }
+    float oacc[NT][4];
+#pragma unroll
+    for (int n = 0; n < NT; ++n) oacc[n][0] = oacc[n][1] = oacc[n][2] = oacc[n][3] = 0.f;
+    float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+
+    for (int sb0 = 0; sb0 < S; sb0 += ksb) {
+        const int nk = min(ksb, S - sb0);
+        const int nk16 = (nk + 15) & ~15;
+        __syncthreads();
+        for (int e = threadIdx.x; e < nk16 * (DH / 8); e += blockDim.x) {
+            const int j = e / (DH / 8), c8 = (e % (DH / 8)) * 8;
+            uint4 kh = make_uint4(0, 0, 0, 0), kl = kh, vh = kh, vl = kh;
+            if (j < nk) {
+                const size_t o = static_cast<size_t>(t0 + sb0 + j) * ld + h * DH + c8;
+                kh = *reinterpret_cast<const uint4*>(ph + o + H);
+                kl = *reinterpret_cast<const uint4*>(pl + o + H);
+                vh = *reinterpret_cast<const uint4*>(ph + o + 2 * H);
+                vl = *reinterpret_cast<const uint4*>(pl + o + 2 * H);
+            }
+            *reinterpret_cast<uint4*>(Kh + j * KSTR + c8) = kh;
+            *reinterpret_cast<uint4*>(Kl + j * KSTR + c8) = kl;
+            *reinterpret_cast<uint4*>(Vh + j * KSTR + c8) = vh;
+            *reinterpret_cast<uint4*>(Vl + j * KSTR + c8) = vl;
+        }
+        __syncthreads();
+        if (!warp_live) continue;
+        for (int kb0 = 0; kb0 < nk16; kb0 += 32) {
+            float sacc[4][4];
+#pragma unroll
+            for (int n = 0; n < 4; ++n) sacc[n][0] = sacc[n][1] = sacc[n][2] = sacc[n][3] = 0.f;
+            const bool full_blk = kb0 + 32 <= nk16;      // else only the first two n-tiles hold keys
+#pragma unroll
+            for (int ks = 0; ks < KS; ++ks) {
+                uint32_t bh[4][2], bl[4][2];
+#pragma unroll
+                for (int n = 0; n < 4; ++n) {
+                    const int key = kb0 + n * 8 + g;     // rows past nk16 are stale smem, masked below
+                    bh[n][0] = *reinterpret_cast<const uint32_t*>(Kh + key * KSTR + ks * 16 + 2 * t);
+                    bh[n][1] = *reinterpret_cast<const uint32_t*>(Kh + key * KSTR + ks * 16 + 2 * t + 8);
+                    bl[n][0] = *reinterpret_cast<const uint32_t*>(Kl + key * KSTR + ks * 16 + 2 * t);
+                    bl[n][1] = *reinterpret_cast<const uint32_t*>(Kl + key * KSTR + ks * 16 + 2 * t + 8);
+                }
+#pragma unroll
+                for (int n = 0; n < 4; ++n) if (n < 2 || full_blk) mma16816(sacc[n], qh[ks], bh[n]);
+#pragma unroll
+                for (int n = 0; n < 4; ++n) if (n < 2 || full_blk) mma16816(sacc[n], ql[ks], bh[n]);
+#pragma unroll
+                for (int n = 0; n < 4; ++n) if (n < 2 || full_blk) mma16816(sacc[n], qh[ks], bl[n]);
+            }
+            float bm0 = -INFINITY, bm1 = -INFINITY;
+#pragma unroll
+            for (int n = 0; n < 4; ++n) {
+                const int k0 = kb0 + n * 8 + 2 * t;
+                if (k0 >= nk) { sacc[n][0] = -INFINITY; sacc[n][2] = -INFINITY; }
+                if (k0 + 1 >= nk) { sacc[n][1] = -INFINITY; sacc[n][3] = -INFINITY; }
+                bm0 = fmaxf(bm0, fmaxf(sacc[n][0], sacc[n][1]));
+                bm1 = fmaxf(bm1, fmaxf(sacc[n][2], sacc[n][3]));
+            }
+            bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffffu, bm0, 1));
+            bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffffu, bm0, 2));
+            bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 1));
+            bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 2));
+            const float mn0 = fmaxf(m0, bm0), mn1 = fmaxf(m1, bm1);
+            const float c0 = fast_exp2(m0 - mn0), c1 = fast_exp2(m1 - mn1);   // scores are pre-scaled by log2(e)
+            m0 = mn0; m1 = mn1;
+            float ps0 = 0.f, ps1 = 0.f;
+#pragma unroll
+            for (int n = 0; n < 4; ++n) {
+                sacc[n][0] = fast_exp2(sacc[n][0] - mn0); sacc[n][1] = fast_exp2(sacc[n][1] - mn0);
+                sacc[n][2] = fast_exp2(sacc[n][2] - mn1); sacc[n][3] = fast_exp2(sacc[n][3] - mn1);
+                ps0 += sacc[n][0] + sacc[n][1];
+                ps1 += sacc[n][2] + sacc[n][3];
+            }
+            l0 = l0 * c0 + ps0;
+            l1 = l1 * c1 + ps1;
+#pragma unroll
+            for (int n = 0; n < NT; ++n) { oacc[n][0] *= c0; oacc[n][1] *= c0; oacc[n][2] *= c1; oacc[n][3] *= c1; }
+#pragma unroll
+            for (int kk = 0; kk < 2; ++kk) {
+                if (kb0 + kk * 16 < nk16) {
+                    uint32_t pfh[4], pfl[4];
+                    split_pack(sacc[2 * kk][0], sacc[2 * kk][1], pfh[0], pfl[0]);
+                    split_pack(sacc[2 * kk][2], sacc[2 * kk][3], pfh[1], pfl[1]);
+                    split_pack(sacc[2 * kk + 1][0], sacc[2 * kk + 1][1], pfh[2], pfl[2]);
+                    split_pack(sacc[2 * kk + 1][2], sacc[2 * kk + 1][3], pfh[3], pfl[3]);
+                    // ldmatrix.x4.trans: matrices (keys 0-7, d-tile n), (keys 8-15, n), (keys 0-7, n+1), (keys 8-15, n+1)
+                    const int krow = kb0 + kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+                    const int dsel = (lane >> 4) * 8;
+                    uint32_t vh4[NT / 2][4], vl4[NT / 2][4];
+#pragma unroll
+                    for (int n2 = 0; n2 < NT / 2; ++n2) {
+                        ldmatrix_x4_trans(vh4[n2], Vh + krow * KSTR + n2 * 16 + dsel);
+                        ldmatrix_x4_trans(vl4[n2], Vl + krow * KSTR + n2 * 16 + dsel);
+                    }
+#pragma unroll
+                    for (int n2 = 0; n2 < NT / 2; ++n2) {
+                        const uint32_t a_[2] = {vh4[n2][0], vh4[n2][1]}, b_[2] = {vh4[n2][2], vh4[n2][3]};
+                        mma16816(oacc[2 * n2], pfh, a_);
+                        mma16816(oacc[2 * n2 + 1], pfh, b_);
+                    }
+#pragma unroll
+                    for (int n2 = 0; n2 < NT / 2; ++n2) {
+                        const uint32_t a_[2] = {vh4[n2][0], vh4[n2][1]}, b_[2] = {vh4[n2][2], vh4[n2][3]};
+                        mma16816(oacc[2 * n2], pfl, a_);
+                        mma16816(oacc[2 * n2 + 1], pfl, b_);
+                    }
+#pragma unroll
+                    for (int n2 = 0; n2 < NT / 2; ++n2) {
+                        const uint32_t a_[2] = {vl4[n2][0], vl4[n2][1]}, b_[2] = {vl4[n2][2], vl4[n2][3]};
+                        mma16816(oacc[2 * n2], pfh, a_);
+                        mma16816(oacc[2 * n2 + 1], pfh, b_);
+                    }
+                }
+            }
+        }
+    }
+    if (!warp_live) return;
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+    const float i0 = 1.0f / l0, i1 = 1.0f / l1;
+    const int ra = r0 + g, rb = r0 + g + 8;
+#pragma unroll
+    for (int n = 0; n < NT; ++n) {
+        const int col = h * DH + n * 8 + 2 * t;
+        uint32_t hi, lo;
+        if (ra < S) {
+            split_pack(oacc[n][0] * i0, oacc[n][1] * i0, hi, lo);
+            *reinterpret_cast<uint32_t*>(ctx_hi + static_cast<size_t>(t0 + ra) * H + col) = hi;
+            *reinterpret_cast<uint32_t*>(ctx_lo + static_cast<size_t>(t0 + ra) * H + col) = lo;
+        }
+        if (rb < S) {
+            split_pack(oacc[n][2] * i1, oacc[n][3] * i1, hi, lo);
+            *reinterpret_cast<uint32_t*>(ctx_hi + static_cast<size_t>(t0 + rb) * H + col) = hi;
+            *reinterpret_cast<uint32_t*>(ctx_lo + static_cast<size_t>(t0 + rb) * H + col) = lo;
+        }
+    }
+}
+
 // sentence-transformers Pooling (mean | cls) + optional Normalize -> out [B, H]
 __global__ void __launch_bounds__(256) pool_kernel(const __half* __restrict__ hi, const __half* __restrict__ lo,
                                                    const int* __restrict__ cu, int H, int mode, int normalize,
@@ -492,7 +717,7 @@ struct rmu_encoder {
     // activations
     int tok_cap = 0, seq_cap = 0;
     std::vector<void*> act_allocs;
-    SplitOperand X, CTX, X1, FF;
+    SplitOperand X, CTX, X1, FF, QKVP;   // QKVP: q (pre-scaled) | k | v as split planes [T, 3H]
     float *QKV = nullptr, *PRE = nullptr;
     int *d_ids = nullptr, *d_typ = nullptr, *d_cu = nullptr;   // staging for the *_host entry points
     float* d_out = nullptr;
@@ -563,6 +788,7 @@ static int ensure_tokens(rmu_encoder* e, int T, int B) {
     if (rc == RMU_OK) rc = planes(&e->CTX, H);
     if (rc == RMU_OK) rc = planes(&e->X1, H);
     if (rc == RMU_OK) rc = planes(&e->FF, F);
+    if (rc == RMU_OK) rc = planes(&e->QKVP, 3 * H);
     if (rc == RMU_OK) rc = dev_alloc(e->act_allocs, &e->QKV, static_cast<size_t>(cap) * 3 * H);
     if (rc == RMU_OK) rc = dev_alloc(e->act_allocs, &e->PRE, static_cast<size_t>(cap) * H);
     if (rc == RMU_OK) rc = dev_alloc(e->act_allocs, &e->d_ids, static_cast<size_t>(cap));
@@ -594,15 +820,39 @@ static int run_encoder(rmu_encoder* e, const int32_t* ids, const int32_t* type_i
     const float scale = 1.0f / sqrtf(static_cast<float>(DH));
     for (int l = 0; l < c.layers; ++l) {
         EncLayer& L = e->layers[l];
+        static const int attn_mode = [] { const char* e = getenv("RMU_ATTN_MODE"); return e ? atoi(e) : 0; }();
         GemmParams g{};
-        g.M = T; g.N = 3 * H; g.K = H; g.bias = L.bqkv; g.out_f32 = e->QKV;
-        rc = launch_gemm(GEMM_BIAS_F32, e->X, L.Wqkv, g, e->sms, st);
+        g.M = T; g.N = 3 * H; g.K = H; g.bias = L.bqkv;
+        if (attn_mode == 0) {
+            // q (scaled by 1/sqrt(dh)), k, v leave the GEMM as split fp16 planes: attention does no conversions
+            // (the softmax runs in base 2: q also carries log2(e))
+            g.out_hi = e->QKVP.hi; g.out_lo = e->QKVP.lo; g.qcols = H; g.qscale = scale * 1.4426950408889634f;
+            rc = launch_gemm(GEMM_BIAS_SPLIT_QSCALE, e->X, L.Wqkv, g, e->sms, st);
+        } else {
+            g.out_f32 = e->QKV;
+            rc = launch_gemm(GEMM_BIAS_F32, e->X, L.Wqkv, g, e->sms, st);
+        }
         if (rc != RMU_OK) return rc;
         dim3 ag(static_cast<unsigned>(B), static_cast<unsigned>(c.heads));
         {
             ProfScope _ps(PROF_ATTN, st);
-            static const bool simt = [] { const char* e = getenv("RMU_ATTN_SIMT"); return e && atoi(e) != 0; }();
-            if (simt) {
+            if (attn_mode == 0) {
+                dim3 pg(static_cast<unsigned>(B), static_cast<unsigned>(c.heads),
+                        static_cast<unsigned>((max_seqlen + kAttWarps * 16 - 1) / (kAttWarps * 16)));
+                // keys resident per CTA: the whole (longest) sequence when it fits, else super-blocks of kKeySB
+                const int ksb = std::min(kKeySB, (max_seqlen + 31) / 32 * 32);
+                const size_t smem_max = 4 * sizeof(__half) * static_cast<size_t>(kKeySB) * (DH + 8);
+                const size_t smem = 4 * sizeof(__half) * static_cast<size_t>(ksb) * (DH + 8);
+                if (DH == 32) {
+                    static bool set32 = false;
+                    if (!set32) { RMU_CUDA(cudaFuncSetAttribute(attention_planes_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_max))); set32 = true; }
+                    attention_planes_kernel<32><<<pg, kAttWarps * 32, smem, st>>>(e->QKVP.hi, e->QKVP.lo, cu, H, ksb, e->CTX.hi, e->CTX.lo);
+                } else {
+                    static bool set64 = false;
+                    if (!set64) { RMU_CUDA(cudaFuncSetAttribute(attention_planes_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_max))); set64 = true; }
+                    attention_planes_kernel<64><<<pg, kAttWarps * 32, smem, st>>>(e->QKVP.hi, e->QKVP.lo, cu, H, ksb, e->CTX.hi, e->CTX.lo);
+                }
+            } else if (attn_mode == 2) {
                 if (DH == 32) attention_kernel<32><<<ag, 128, 0, st>>>(e->QKV, cu, H, scale, e->CTX.hi, e->CTX.lo);
                 else attention_kernel<64><<<ag, 128, 0, st>>>(e->QKV, cu, H, scale, e->CTX.hi, e->CTX.lo);
             } else {

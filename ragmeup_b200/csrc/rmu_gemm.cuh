@@ -9,7 +9,7 @@
 // K step issues three tcgen05.mma kind::f16: hi*hi + lo*hi + hi*lo, fp32 accumulate in TMEM.
 //
 // Kernel shape: persistent, 1 CTA/SM, 192 threads = TMA producer warp, MMA issuer warp (one lane)
-// + TMEM allocator, 4 epilogue warps.  128x128 output tiles, K blocks of 64 (one 128-byte swizzled
+// + TMEM allocator, 8 epilogue warps.  128x128 output tiles, K blocks of 64 (one 128-byte swizzled
 // row per operand row), 3-stage smem ring (4 planes x 16 KB per stage), two TMEM accumulator
 // buffers so the epilogue of tile i overlaps the MMAs of tile i+1.
 #pragma once
@@ -21,13 +21,17 @@ namespace rmu {
 constexpr int kGemmBM = 128, kGemmBN = 128, kGemmBK = 64, kGemmStages = 3;
 constexpr int kGemmPlaneBytes = 128 * 128;                 // 128 rows x 128 B
 constexpr int kGemmStageBytes = 4 * kGemmPlaneBytes;       // Ahi, Alo, Whi, Wlo
-constexpr int kGemmThreads = 192;
-constexpr size_t kGemmSmem = static_cast<size_t>(kGemmStages) * kGemmStageBytes + 256 + 1024;
+constexpr int kGemmEpiWarps = 8;                           // two per TMEM lane quadrant, each takes half the columns
+constexpr int kGemmThreads = 64 + 32 * kGemmEpiWarps;      // + TMA producer warp + MMA issuer warp
+constexpr int kGemmStageRow = 33;                          // padded row of the per-warp [32][32] staging tile
+constexpr size_t kGemmStagingBytes = static_cast<size_t>(kGemmEpiWarps) * 32 * kGemmStageRow * sizeof(float);
+constexpr size_t kGemmSmem = static_cast<size_t>(kGemmStages) * kGemmStageBytes + kGemmStagingBytes + 256 + 1024;
 
 enum GemmMode {
     GEMM_BIAS_F32 = 0,        // out_f32 = acc + bias
     GEMM_BIAS_GELU_SPLIT = 1, // out planes = split(gelu_erf(acc + bias))
     GEMM_BIAS_RESID_F32 = 2,  // out_f32 = acc + bias + (res_hi + res_lo)
+    GEMM_BIAS_SPLIT_QSCALE = 3, // out planes = split((acc + bias) * (col < qcols ? qscale : 1))   (QKV projection)
 };
 
 struct GemmParams {
@@ -36,6 +40,7 @@ struct GemmParams {
     float* out_f32;                       // [M, N]
     __half* out_hi; __half* out_lo;       // [M, N]
     const __half* res_hi; const __half* res_lo;  // [M, N]
+    int qcols; float qscale;              // GEMM_BIAS_SPLIT_QSCALE
 };
 
 __device__ __forceinline__ void split_f16(float v, __half& hi, __half& lo) {
@@ -43,7 +48,19 @@ __device__ __forceinline__ void split_f16(float v, __half& hi, __half& lo) {
     lo = __float2half_rn(v - __half2float(hi));
 }
 
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+// erf by Abramowitz & Stegun 7.1.26 (|error| <= 1.5e-7, the fp32 noise floor of the erf-GELU the
+// reference computes with torch.erf) on the fast exp / reciprocal units: the FFN-in epilogue is ALU-bound.
+__device__ __forceinline__ float erf_as(float x) {
+    const float ax = fabsf(x);
+    const float t = __fdividef(1.0f, fmaf(0.3275911f, ax, 1.0f));
+    float p = fmaf(1.061405429f, t, -1.453152027f);
+    p = fmaf(p, t, 1.421413741f);
+    p = fmaf(p, t, -0.284496736f);
+    p = fmaf(p, t, 0.254829592f);
+    const float y = 1.0f - p * t * __expf(-ax * ax);
+    return copysignf(y, x);
+}
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erf_as(x * 0.70710678118654752440f)); }
 
 template <int MODE>
 __global__ void __launch_bounds__(kGemmThreads, 1)
@@ -53,7 +70,8 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tAh, const __grid_constant
     constexpr uint32_t IDESC = umma_idesc(0 /*f16*/, kGemmBM, kGemmBN);
     extern __shared__ uint8_t gemm_smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(gemm_smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + kGemmStages * kGemmStageBytes);
+    float* staging = reinterpret_cast<float*>(smem + kGemmStages * kGemmStageBytes);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + kGemmStages * kGemmStageBytes + kGemmStagingBytes);
     uint64_t* empty = full + kGemmStages;
     uint64_t* acc_full = empty + kGemmStages;
     uint64_t* acc_empty = acc_full + 2;
@@ -63,7 +81,7 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tAh, const __grid_constant
     const unsigned lane = lane_id();
     if (threadIdx.x == 0) {
         for (int i = 0; i < kGemmStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 128); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 32 * kGemmEpiWarps); }
         fence_mbar_init();
         prefetch_tmap(&tAh); prefetch_tmap(&tAl); prefetch_tmap(&tWh); prefetch_tmap(&tWl);
     }
@@ -129,7 +147,14 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tAh, const __grid_constant
             }
         }
     } else {
+        // ---- epilogue: warp (2 + ew) reads TMEM lanes of quadrant (warp & 3); ew < 4 takes column chunks 0-1
+        //      of the tile, ew >= 4 chunks 2-3.  Values are staged through a per-warp smem tile so that every
+        //      global access (output rows, residual rows) is a fully used, coalesced row segment.
+        const int ew = warp - 2;
         const int quad = warp & 3;
+        const int chalf = ew >> 2;
+        float* stg = staging + ew * (32 * kGemmStageRow);
+        const int rsub = static_cast<int>(lane) >> 4, cp = (static_cast<int>(lane) & 15) * 2;
         int i = 0;
         for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++i) {
             const int mb = tile / n_blks, nb = tile % n_blks;
@@ -137,63 +162,67 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tAh, const __grid_constant
             const uint32_t use = static_cast<uint32_t>(i >> 1);
             mbar_wait(&acc_full[buf], use & 1);
             tc_fence_after();
-            const int row = mb * kGemmBM + quad * 32 + static_cast<int>(lane);
-            const bool row_ok = row < p.M;
+            const int row_base = mb * kGemmBM + quad * 32;
 #pragma unroll 1
-            for (int c = 0; c < kGemmBN / 32; ++c) {
-                uint32_t r[32];
-                tmem_ld32(tmem_addr(tmem_base, quad * 32, buf * kGemmBN + c * 32), r);
-                tmem_ld_wait();
+            for (int cc = 0; cc < 2; ++cc) {
+                const int c = chalf * 2 + cc;
                 const int col0 = nb * kGemmBN + c * 32;
-                float v[32];
+                // residual rows of this chunk: issued first so their latency hides behind the TMEM read
+                __half2 rsh[16], rsl[16];
+                if (MODE == GEMM_BIAS_RESID_F32) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + __ldg(p.bias + col0 + j);
-                if (row_ok) {
-                    const size_t o = static_cast<size_t>(row) * p.N + col0;
-                    if (MODE == GEMM_BIAS_RESID_F32) {
-                        const uint4* rh = reinterpret_cast<const uint4*>(p.res_hi + o);
-                        const uint4* rl = reinterpret_cast<const uint4*>(p.res_lo + o);
-#pragma unroll
-                        for (int g = 0; g < 4; ++g) {
-                            uint4 a = __ldg(rh + g), b = __ldg(rl + g);
-                            const __half2* ah = reinterpret_cast<const __half2*>(&a);
-                            const __half2* bl = reinterpret_cast<const __half2*>(&b);
-#pragma unroll
-                            for (int e = 0; e < 4; ++e) {
-                                float2 fa = __half22float2(ah[e]), fb = __half22float2(bl[e]);
-                                v[g * 8 + e * 2] += fa.x + fb.x;
-                                v[g * 8 + e * 2 + 1] += fa.y + fb.y;
-                            }
-                        }
-                    }
-                    if (MODE == GEMM_BIAS_F32 || MODE == GEMM_BIAS_RESID_F32) {
-                        float4* dst = reinterpret_cast<float4*>(p.out_f32 + o);
-#pragma unroll
-                        for (int g = 0; g < 8; ++g) dst[g] = make_float4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
-                    } else {
-                        uint4* dh = reinterpret_cast<uint4*>(p.out_hi + o);
-                        uint4* dl = reinterpret_cast<uint4*>(p.out_lo + o);
-#pragma unroll
-                        for (int g = 0; g < 4; ++g) {
-                            uint4 ph, pl;
-                            __half2* hh = reinterpret_cast<__half2*>(&ph);
-                            __half2* ll = reinterpret_cast<__half2*>(&pl);
-#pragma unroll
-                            for (int e = 0; e < 4; ++e) {
-                                __half h0, l0, h1, l1;
-                                split_f16(gelu_erf(v[g * 8 + e * 2]), h0, l0);
-                                split_f16(gelu_erf(v[g * 8 + e * 2 + 1]), h1, l1);
-                                hh[e] = __halves2half2(h0, h1);
-                                ll[e] = __halves2half2(l0, l1);
-                            }
-                            dh[g] = ph;
-                            dl[g] = pl;
+                    for (int q = 0; q < 16; ++q) {
+                        const int grow = row_base + 2 * q + rsub;
+                        if (grow < p.M) {
+                            const size_t o = static_cast<size_t>(grow) * p.N + col0 + cp;
+                            rsh[q] = *reinterpret_cast<const __half2*>(p.res_hi + o);
+                            rsl[q] = *reinterpret_cast<const __half2*>(p.res_lo + o);
                         }
                     }
                 }
+                uint32_t r[32];
+                tmem_ld32(tmem_addr(tmem_base, quad * 32, buf * kGemmBN + c * 32), r);
+                tmem_ld_wait();
+                if (cc == 1) {                       // last TMEM read of this warp for the tile
+                    tc_fence_before();
+                    mbar_arrive(&acc_empty[buf]);
+                }
+                const float bia = __ldg(p.bias + col0 + lane);
+                const float sc = (MODE == GEMM_BIAS_SPLIT_QSCALE && col0 < p.qcols) ? p.qscale : 1.0f;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    float v = __uint_as_float(r[j]) + __shfl_sync(0xffffffffu, bia, j);
+                    if (MODE == GEMM_BIAS_GELU_SPLIT) v = gelu_erf(v);
+                    if (MODE == GEMM_BIAS_SPLIT_QSCALE) v *= sc;
+                    stg[lane * kGemmStageRow + j] = v;
+                }
+                __syncwarp();
+#pragma unroll
+                for (int rr = 0; rr < 32; rr += 2) {
+                    const int rl = rr + rsub;
+                    const int grow = row_base + rl;
+                    if (grow < p.M) {
+                        float a = stg[rl * kGemmStageRow + cp], b = stg[rl * kGemmStageRow + cp + 1];
+                        const size_t o = static_cast<size_t>(grow) * p.N + col0 + cp;
+                        if (MODE == GEMM_BIAS_RESID_F32) {
+                            const float2 fh = __half22float2(rsh[rr >> 1]);
+                            const float2 fl = __half22float2(rsl[rr >> 1]);
+                            a += fh.x + fl.x;
+                            b += fh.y + fl.y;
+                        }
+                        if (MODE == GEMM_BIAS_F32 || MODE == GEMM_BIAS_RESID_F32) {
+                            *reinterpret_cast<float2*>(p.out_f32 + o) = make_float2(a, b);
+                        } else {
+                            __half h0, l0, h1, l1;
+                            split_f16(a, h0, l0);
+                            split_f16(b, h1, l1);
+                            *reinterpret_cast<__half2*>(p.out_hi + o) = __halves2half2(h0, h1);
+                            *reinterpret_cast<__half2*>(p.out_lo + o) = __halves2half2(l0, l1);
+                        }
+                    }
+                }
+                __syncwarp();
             }
-            tc_fence_before();
-            mbar_arrive(&acc_empty[buf]);
         }
     }
     tc_fence_before();

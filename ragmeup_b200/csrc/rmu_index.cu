@@ -186,12 +186,12 @@ struct ScanParams {
     unsigned long long* lists;  // [gridDim.x][128][2*KEEP]
     float* dbg;            // diagnostics: CTA 0 dumps the raw accumulators of its first tile [128][BN]
     int ablate;            // profiling only: bit0 skip MMA issue, bit1 skip epilogue work, bit2 skip TMEM loads
-    // threshold exchange: phase 0 = whole range in one launch; phase 1 = only the first `lead` tiles of
-    // every CTA (leaves sorted lists + counts); phase 2 = the rest, starting from the lists of phase 1 and
-    // the per-query global threshold tau0 (KEEP-th best key over ALL CTAs' phase-1 lists).
+    // threshold exchange: phase 0 = whole range, thresholds start at -inf; phase 1 = only the first `lead`
+    // tiles of every CTA, run with a small KEEP purely to estimate thresholds; phase 2 = whole range again,
+    // every query starting from tau0 = the KEEP-th best key over the union of all CTAs' phase-1 lists (a
+    // subset of the rows, hence a valid lower bound of the final KEEP-th best key).
     int phase, lead;
     const float* tau0;     // [nq_total]
-    int* counts;           // [gridDim.x][128]
 };
 
 // BN rows per tile (= MMA N), NBUF TMEM accumulators, NSLAB pipeline stages, each stage = KD K-blocks
@@ -234,7 +234,6 @@ scan_tf32_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
     int t0 = static_cast<int>((static_cast<long long>(blockIdx.x) * p.ntiles) / gridDim.x);
     int t1 = static_cast<int>((static_cast<long long>(blockIdx.x + 1) * p.ntiles) / gridDim.x);
     if (p.phase == 1) t1 = min(t1, t0 + p.lead);
-    if (p.phase == 2) t0 = min(t1, t0 + p.lead);
 
     // ---- query block -> TMEM (A operand): lane = query, column = dimension, zero padded
     const int quad = warp & 3;  // TMEM lane quadrant this warp may touch
@@ -320,11 +319,7 @@ scan_tf32_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
         unsigned long long* mybuf = p.lists + (static_cast<long long>(blockIdx.x) * kScanQ + qi) * CAP;
         int cnt = 0;
         float tau = live ? -INFINITY : INFINITY;
-        if (p.phase == 2 && live) {
-            cnt = p.counts[blockIdx.x * kScanQ + qi];
-            if (cnt >= KEEP) tau = key_score(mybuf[KEEP - 1]);
-            tau = fmaxf(tau, p.tau0[p.q0 + qi]);
-        }
+        if (p.phase == 2 && live) tau = p.tau0[p.q0 + qi];
         const bool has_sb = (p.rscale != nullptr) || (p.rbias != nullptr);
         for (int t = t0; t < t1; ++t) {
             const int i = t - t0;
@@ -390,7 +385,6 @@ scan_tf32_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
         // final: every list sorted descending, zero padded to KEEP entries
         warp_compact<KEEP>(mybuf, cnt, tau, true);
         for (int e = cnt; e < KEEP; ++e) mybuf[e] = 0ull;
-        if (p.phase == 1) p.counts[blockIdx.x * kScanQ + qi] = cnt;
     }
 
     tc_fence_before();
@@ -907,6 +901,7 @@ static int dispatch_variant(const CUtensorMap& tmap, const ScanParams& p, int gr
 
 static int dispatch_scan(int keep, const CUtensorMap& tmap, const ScanParams& p, int grid, cudaStream_t st) {
     switch (keep) {
+        case 32: return dispatch_variant<32>(tmap, p, grid, st);
         case 64: return dispatch_variant<64>(tmap, p, grid, st);
         case 128: return dispatch_variant<128>(tmap, p, grid, st);
         case 256: return dispatch_variant<256>(tmap, p, grid, st);
@@ -1032,7 +1027,6 @@ int rmu_index_search(rmu_index* idx, const float* queries, int nq, int k, int64_
     const size_t o_nsel = carve(sizeof(int) * 4);
     const size_t o_scan = tensor_ok ? carve(sizeof(unsigned long long) * grid_scan * kScanQ * 2 * keep) : 0;
     const size_t o_tau = carve(sizeof(float) * nq);
-    const size_t o_cnt = carve(sizeof(int) * grid_scan * kScanQ);
     const size_t o_exact = carve(sizeof(unsigned long long) * std::max(nchunks, 1) * static_cast<size_t>(nq) * keepx);
     int rc = ensure_ws(idx, off);
     if (rc != RMU_OK) return rc;
@@ -1043,7 +1037,6 @@ int rmu_index_search(rmu_index* idx, const float* queries, int nq, int k, int64_
     unsigned long long* d_scan = reinterpret_cast<unsigned long long*>(ws + o_scan);
     unsigned long long* d_exact = reinterpret_cast<unsigned long long*>(ws + o_exact);
     float* d_tau0 = reinterpret_cast<float*>(ws + o_tau);
-    int* d_cnt = reinterpret_cast<int*>(ws + o_cnt);
 
     const size_t qsmem = static_cast<size_t>(D) * sizeof(float);
     int scan_launches = 0;
@@ -1084,19 +1077,22 @@ int rmu_index_search(rmu_index* idx, const float* queries, int nq, int k, int64_
             sp.lists = d_scan;
             { static const char* ab = getenv("RMU_SCAN_ABLATE"); sp.ablate = ab ? atoi(ab) : 0; }
             const int grid = std::min(grid_scan, ntiles);
-            // threshold exchange (big corpora): every CTA first scans a lead of its range, the per-query
-            // KEEP-th best over all CTAs becomes the starting threshold of the main pass
-            static const int lead_pct = [] { const char* e = getenv("RMU_SCAN_LEAD_PCT"); return e ? atoi(e) : 6; }();
+            // threshold exchange (big corpora): a cheap lead pass (first ~2 % of every CTA's tiles, KEEP = 32)
+            // estimates per-query thresholds, then the full pass starts from them, so its epilogue almost
+            // never takes the insert path.  The lead rows are read twice (+2 % traffic).
+            static const int lead_env = [] { const char* e = getenv("RMU_SCAN_LEAD_PCT"); return e ? atoi(e) : -1; }();
+            const int lead_pct = lead_env >= 0 ? lead_env : 2;
             const int tiles_per_cta = ntiles / grid;
-            const bool exchange = lead_pct > 0 && tiles_per_cta >= 16;
-            sp.tau0 = d_tau0; sp.counts = d_cnt;
+            constexpr int kLeadKeep = 32;
+            const bool exchange = lead_pct > 0 && tiles_per_cta >= 16 && grid * kLeadKeep >= keep;
+            sp.tau0 = d_tau0;
             if (exchange) {
                 sp.phase = 1;
                 sp.lead = std::max(2, (tiles_per_cta * lead_pct + 99) / 100);
-                rc = dispatch_scan(keep, idx->tmap, sp, grid, st);
+                rc = dispatch_scan(kLeadKeep, idx->tmap, sp, grid, st);
                 if (rc != RMU_OK) return rc;
                 { ProfScope _ps(PROF_FINALIZE, st);
-                select_tau_kernel<<<sp.nq, 256, 0, st>>>(d_scan, grid, 2 * keep, keep, keep, q0, d_tau0); }
+                select_tau_kernel<<<sp.nq, 256, 0, st>>>(d_scan, grid, 2 * kLeadKeep, kLeadKeep, keep, q0, d_tau0); }
                 count_launch();
                 RMU_CHECK_LAUNCH();
                 sp.phase = 2;
