@@ -48,7 +48,7 @@ PAIR_LEN = Q_TOK + D_TOK + 3                    # [CLS] q [SEP] d [SEP] = 147
 DOC_TABLE = 65536                               # distinct synthetic documents' token rows
 CHUNK = 250_000                                 # corpus generation granularity (seed per global chunk)
 METRIC = os.environ.get("BENCH_METRIC", "cosine")
-CE_CHUNK = int(os.environ.get("BENCH_CE_CHUNK", 400))      # rerank pairs per encoder call (58.8k tokens)
+CE_CHUNK = int(os.environ.get("BENCH_CE_CHUNK", 800))      # rerank pairs per encoder call (117.6k tokens, ~2 GB of activations)
 
 
 def peaks():

@@ -31,13 +31,14 @@ int make_tmap_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t col
     if (elem_bytes == 4) dt = CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
     else if (elem_bytes == 2) dt = CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
     else { set_error("make_tmap_2d: bad element size"); return RMU_ERR_ARG; }
-    if (box_cols * elem_bytes != 128) { set_error("make_tmap_2d: box must be 128 bytes wide"); return RMU_ERR_ARG; }
+    const uint32_t box_bytes = box_cols * elem_bytes;
+    if (box_bytes != 128 && box_bytes != 64) { set_error("make_tmap_2d: box must be 128 or 64 bytes wide"); return RMU_ERR_ARG; }
     cuuint64_t gdim[2] = {cols, rows};
     cuuint64_t gstride[1] = {row_stride_bytes};
     cuuint32_t box[2] = {box_cols, box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(out, dt, 2, const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     box_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_error("cuTensorMapEncodeTiled failed with CUresult " + std::to_string(static_cast<int>(r)));

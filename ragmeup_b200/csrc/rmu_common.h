@@ -55,7 +55,7 @@ PFN_encodeTiled get_encode_tiled();
 
 // 2-D row-major [rows, cols] tensor of `elem_bytes` elements, box {box_cols, box_rows}, 128-B swizzle.
 int make_tmap_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t row_stride_bytes,
-                 uint32_t box_cols, uint32_t box_rows, int elem_bytes);
+                 uint32_t box_cols, uint32_t box_rows, int elem_bytes);   // box 128 B wide (SWIZZLE_128B) or 64 B (SWIZZLE_64B)
 
 // fp32 row-major [rows, 32*kblocks] viewed as (32 floats, rows, kblock) so that ONE box
 // {32, box_rows, box_kb} lands in smem as box_kb consecutive K-major 128-B-swizzled slabs.

@@ -758,7 +758,7 @@ static int upload_split(rmu_encoder* e, SplitOperand* op, const std::vector<cons
     cudaError_t err = cudaDeviceSynchronize();
     cudaFree(tmp);
     if (err != cudaSuccess) { set_error(std::string("split_planes: ") + cudaGetErrorString(err)); return RMU_ERR_CUDA; }
-    return make_split_operand(op, hi, lo, static_cast<int64_t>(rows), cols);
+    return make_split_operand(op, hi, lo, static_cast<int64_t>(rows), cols, /*is_activation=*/false);
 }
 
 static void free_acts(rmu_encoder* e) {
@@ -782,7 +782,7 @@ static int ensure_tokens(rmu_encoder* e, int T, int B) {
         if (rc != RMU_OK) return rc;
         RMU_CUDA(cudaMemset(hi, 0, static_cast<size_t>(cap) * cols * sizeof(__half)));
         RMU_CUDA(cudaMemset(lo, 0, static_cast<size_t>(cap) * cols * sizeof(__half)));
-        return make_split_operand(op, hi, lo, cap, cols);
+        return make_split_operand(op, hi, lo, cap, cols, /*is_activation=*/true);
     };
     int rc = planes(&e->X, H);
     if (rc == RMU_OK) rc = planes(&e->CTX, H);

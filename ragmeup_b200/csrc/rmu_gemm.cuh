@@ -180,6 +180,7 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tAh, const __grid_constant
                         }
                     }
                 }
+                const float2 bia2 = __ldg(reinterpret_cast<const float2*>(p.bias + col0 + cp));
                 uint32_t r[32];
                 tmem_ld32(tmem_addr(tmem_base, quad * 32, buf * kGemmBN + c * 32), r);
                 tmem_ld_wait();
@@ -187,22 +188,19 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tAh, const __grid_constant
                     tc_fence_before();
                     mbar_arrive(&acc_empty[buf]);
                 }
-                const float bia = __ldg(p.bias + col0 + lane);
                 const float sc = (MODE == GEMM_BIAS_SPLIT_QSCALE && col0 < p.qcols) ? p.qscale : 1.0f;
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    float v = __uint_as_float(r[j]) + __shfl_sync(0xffffffffu, bia, j);
-                    if (MODE == GEMM_BIAS_GELU_SPLIT) v = gelu_erf(v);
-                    if (MODE == GEMM_BIAS_SPLIT_QSCALE) v *= sc;
-                    stg[lane * kGemmStageRow + j] = v;
-                }
+                for (int j = 0; j < 32; ++j) stg[lane * kGemmStageRow + j] = __uint_as_float(r[j]);
                 __syncwarp();
 #pragma unroll
                 for (int rr = 0; rr < 32; rr += 2) {
                     const int rl = rr + rsub;
                     const int grow = row_base + rl;
                     if (grow < p.M) {
-                        float a = stg[rl * kGemmStageRow + cp], b = stg[rl * kGemmStageRow + cp + 1];
+                        // lane = column pair: the bias is a per-lane constant of the chunk
+                        float a = stg[rl * kGemmStageRow + cp] + bia2.x, b = stg[rl * kGemmStageRow + cp + 1] + bia2.y;
+                        if (MODE == GEMM_BIAS_GELU_SPLIT) { a = gelu_erf(a); b = gelu_erf(b); }
+                        if (MODE == GEMM_BIAS_SPLIT_QSCALE) { a *= sc; b *= sc; }
                         const size_t o = static_cast<size_t>(grow) * p.N + col0 + cp;
                         if (MODE == GEMM_BIAS_RESID_F32) {
                             const float2 fh = __half22float2(rsh[rr >> 1]);
@@ -231,16 +229,210 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tAh, const __grid_constant
     if (warp == 1) tmem_dealloc<256>(tmem_base);
 }
 
+
+template <int BK>
+__device__ __forceinline__ uint64_t wide_desc(uint32_t smem_addr) {
+    return BK == 32 ? umma_desc_sw64_kmajor(smem_addr) : umma_desc_sw128_kmajor(smem_addr);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Wide variant: 256 x 128 output tile per CTA = two M=128 MMAs per K step sharing the W slab, K blocks of
+// 32 (64-byte swizzled rows) so that FOUR 48 KB stages fit: 26 % less L2->SM traffic per MMA cycle and
+// 50 % more latency cover than the 128x128x64 kernel.  Same roles, same epilogues.
+// ---------------------------------------------------------------------------------------------------
+constexpr int kWideBM = 256, kWideBN = 128;
+// BK = 32: rows of 64 B (SWIZZLE_64B), 4 stages of 48 KB.  BK = 64: rows of 128 B (SWIZZLE_128B), 2 stages of 96 KB.
+constexpr size_t kWideSmem = 196608 + kGemmStagingBytes + 256 + 1024;
+
+template <int MODE, int BK>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_f16x3_wide_kernel(const __grid_constant__ CUtensorMap tAh, const __grid_constant__ CUtensorMap tAl,
+                       const __grid_constant__ CUtensorMap tWh, const __grid_constant__ CUtensorMap tWl,
+                       const GemmParams p) {
+    constexpr uint32_t IDESC = umma_idesc(0 /*f16*/, 128, kWideBN);
+    constexpr int kWideBK = BK;
+    constexpr int kRowBytes = BK * 2;
+    constexpr int kWideStages = BK == 32 ? 4 : 2;
+    constexpr int kWideABytes = 256 * kRowBytes;               // one A plane of a stage
+    constexpr int kWideWBytes = 128 * kRowBytes;               // one W plane of a stage
+    constexpr int kWideStageBytes = 2 * kWideABytes + 2 * kWideWBytes;
+    extern __shared__ uint8_t gemm_smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(gemm_smem_raw) + 1023) & ~uintptr_t(1023));
+    float* staging = reinterpret_cast<float*>(smem + kWideStages * kWideStageBytes);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + kWideStages * kWideStageBytes + kGemmStagingBytes);
+    uint64_t* empty = full + kWideStages;
+    uint64_t* acc_full = empty + kWideStages;
+    uint64_t* acc_empty = acc_full + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const unsigned lane = lane_id();
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < kWideStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 32 * kGemmEpiWarps); }
+        fence_mbar_init();
+        prefetch_tmap(&tAh); prefetch_tmap(&tAl); prefetch_tmap(&tWh); prefetch_tmap(&tWl);
+    }
+    if (warp == 1) tmem_alloc<512>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int m_blks = (p.M + kWideBM - 1) / kWideBM;
+    const int n_blks = p.N / kWideBN;
+    const int k_blks = p.K / kWideBK;
+    const int tiles = m_blks * n_blks;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int slot = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+                const int mb = tile / n_blks, nb = tile % n_blks;
+                for (int kb = 0; kb < k_blks; ++kb) {
+                    mbar_wait(&empty[slot], phase ^ 1);
+                    uint8_t* st = smem + slot * kWideStageBytes;
+                    mbar_arrive_expect_tx(&full[slot], kWideStageBytes);
+                    tma_load_2d(st, &tAh, kb * kWideBK, mb * kWideBM, &full[slot], kEvictNormal);
+                    tma_load_2d(st + kWideABytes, &tAl, kb * kWideBK, mb * kWideBM, &full[slot], kEvictNormal);
+                    tma_load_2d(st + 2 * kWideABytes, &tWh, kb * kWideBK, nb * kWideBN, &full[slot], kEvictLast);
+                    tma_load_2d(st + 2 * kWideABytes + kWideWBytes, &tWl, kb * kWideBK, nb * kWideBN, &full[slot], kEvictLast);
+                    if (++slot == kWideStages) { slot = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            int slot = 0;
+            uint32_t phase = 0;
+            int i = 0;
+            for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++i) {
+                const int buf = i & 1;
+                const uint32_t use = static_cast<uint32_t>(i >> 1);
+                mbar_wait(&acc_empty[buf], (use & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t d0 = tmem_base + buf * 256, d1 = d0 + 128;     // rows 0-127 / 128-255 of the tile
+                for (int kb = 0; kb < k_blks; ++kb) {
+                    mbar_wait(&full[slot], phase);
+                    tc_fence_after();
+                    const uint32_t sbase = smem_u32(smem + slot * kWideStageBytes);
+                    const uint64_t dAh0 = wide_desc<BK>(sbase);
+                    const uint64_t dAh1 = wide_desc<BK>(sbase + 128 * kRowBytes);
+                    const uint64_t dAl0 = wide_desc<BK>(sbase + kWideABytes);
+                    const uint64_t dAl1 = wide_desc<BK>(sbase + kWideABytes + 128 * kRowBytes);
+                    const uint64_t dWh = wide_desc<BK>(sbase + 2 * kWideABytes);
+                    const uint64_t dWl = wide_desc<BK>(sbase + 2 * kWideABytes + kWideWBytes);
+#pragma unroll
+                    for (int k = 0; k < kWideBK / 16; ++k) {
+                        const uint64_t off = static_cast<uint64_t>(k * 2);
+                        const uint32_t acc = (kb | k) != 0 ? 1u : 0u;
+                        mma_f16_ss(d0, dAh0 + off, dWh + off, IDESC, acc);
+                        mma_f16_ss(d1, dAh1 + off, dWh + off, IDESC, acc);
+                        mma_f16_ss(d0, dAl0 + off, dWh + off, IDESC, 1u);
+                        mma_f16_ss(d1, dAl1 + off, dWh + off, IDESC, 1u);
+                        mma_f16_ss(d0, dAh0 + off, dWl + off, IDESC, 1u);
+                        mma_f16_ss(d1, dAh1 + off, dWl + off, IDESC, 1u);
+                    }
+                    tc_commit(&empty[slot]);
+                    if (++slot == kWideStages) { slot = 0; phase ^= 1; }
+                }
+                tc_commit(&acc_full[buf]);
+            }
+        }
+    } else {
+        // epilogue warp (2 + ew): TMEM lane quadrant (warp & 3), tile row half (ew >> 2), all four column chunks
+        const int ew = warp - 2;
+        const int quad = warp & 3;
+        const int mh = ew >> 2;
+        float* stg = staging + ew * (32 * kGemmStageRow);
+        const int rsub = static_cast<int>(lane) >> 4, cp = (static_cast<int>(lane) & 15) * 2;
+        int i = 0;
+        for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++i) {
+            const int mb = tile / n_blks, nb = tile % n_blks;
+            const int buf = i & 1;
+            const uint32_t use = static_cast<uint32_t>(i >> 1);
+            mbar_wait(&acc_full[buf], use & 1);
+            tc_fence_after();
+            const int row_base = mb * kWideBM + mh * 128 + quad * 32;
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c) {
+                const int col0 = nb * kWideBN + c * 32;
+                __half2 rsh[16], rsl[16];
+                if (MODE == GEMM_BIAS_RESID_F32) {
+#pragma unroll
+                    for (int q = 0; q < 16; ++q) {
+                        const int grow = row_base + 2 * q + rsub;
+                        if (grow < p.M) {
+                            const size_t o = static_cast<size_t>(grow) * p.N + col0 + cp;
+                            rsh[q] = *reinterpret_cast<const __half2*>(p.res_hi + o);
+                            rsl[q] = *reinterpret_cast<const __half2*>(p.res_lo + o);
+                        }
+                    }
+                }
+                const float2 bia2 = __ldg(reinterpret_cast<const float2*>(p.bias + col0 + cp));
+                uint32_t r[32];
+                tmem_ld32(tmem_addr(tmem_base, quad * 32, buf * 256 + mh * 128 + c * 32), r);
+                tmem_ld_wait();
+                if (c == 3) {
+                    tc_fence_before();
+                    mbar_arrive(&acc_empty[buf]);
+                }
+                const float sc = (MODE == GEMM_BIAS_SPLIT_QSCALE && col0 < p.qcols) ? p.qscale : 1.0f;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) stg[lane * kGemmStageRow + j] = __uint_as_float(r[j]);
+                __syncwarp();
+#pragma unroll
+                for (int rr = 0; rr < 32; rr += 2) {
+                    const int rl = rr + rsub;
+                    const int grow = row_base + rl;
+                    if (grow < p.M) {
+                        // lane = column pair: the bias is a per-lane constant of the chunk
+                        float a = stg[rl * kGemmStageRow + cp] + bia2.x, b = stg[rl * kGemmStageRow + cp + 1] + bia2.y;
+                        if (MODE == GEMM_BIAS_GELU_SPLIT) { a = gelu_erf(a); b = gelu_erf(b); }
+                        if (MODE == GEMM_BIAS_SPLIT_QSCALE) { a *= sc; b *= sc; }
+                        const size_t o = static_cast<size_t>(grow) * p.N + col0 + cp;
+                        if (MODE == GEMM_BIAS_RESID_F32) {
+                            const float2 fh = __half22float2(rsh[rr >> 1]);
+                            const float2 fl = __half22float2(rsl[rr >> 1]);
+                            a += fh.x + fl.x;
+                            b += fh.y + fl.y;
+                        }
+                        if (MODE == GEMM_BIAS_F32 || MODE == GEMM_BIAS_RESID_F32) {
+                            *reinterpret_cast<float2*>(p.out_f32 + o) = make_float2(a, b);
+                        } else {
+                            __half h0, l0, h1, l1;
+                            split_f16(a, h0, l0);
+                            split_f16(b, h1, l1);
+                            *reinterpret_cast<__half2*>(p.out_hi + o) = __halves2half2(h0, h1);
+                            *reinterpret_cast<__half2*>(p.out_lo + o) = __halves2half2(l0, l1);
+                        }
+                    }
+                }
+                __syncwarp();
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (warp == 1) tmem_dealloc<512>(tmem_base);
+}
+
 // A K-major fp16 operand carried as two planes, with the TMA maps of both
 struct SplitOperand {
     __half* hi = nullptr;
     __half* lo = nullptr;
     int64_t rows = 0;     // rows covered by the tensor maps (allocation rows)
     int cols = 0;
-    CUtensorMap map_hi{}, map_lo{};
+    CUtensorMap map_hi{}, map_lo{};          // box {64 halves, 128 rows}, SWIZZLE_128B  (128x128x64 kernel)
+    CUtensorMap map64_hi{}, map64_lo{};      // box {32 halves, box64_rows}, SWIZZLE_64B (256x128x32 kernel)
+    CUtensorMap mapw_hi{}, mapw_lo{};        // box {64 halves, box64_rows}, SWIZZLE_128B (256x128x64 kernel)
+    int box64_rows = 0;
 };
 
-int make_split_operand(SplitOperand* op, __half* hi, __half* lo, int64_t rows, int cols);
+// is_activation: operand is the A side (256-row boxes for the wide kernel) rather than a weight (128-row boxes)
+int make_split_operand(SplitOperand* op, __half* hi, __half* lo, int64_t rows, int cols, bool is_activation);
 // C = A * W^T with the epilogue `mode`; A rows used = p.M (<= A.rows)
 int launch_gemm(int mode, const SplitOperand& A, const SplitOperand& W, const GemmParams& p, int sms, cudaStream_t st);
 

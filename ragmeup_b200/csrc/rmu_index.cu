@@ -137,9 +137,9 @@ __device__ __forceinline__ void warp_bitonic_desc(unsigned long long (&v)[E]) {
 
 // Warp-cooperative compaction of the per-thread (= per-query) candidate lists of the lanes that ask
 // for it: sort the list descending, keep the best KEEP, raise that lane's threshold.
-template <int KEEP>
+template <int KEEP, int CAP>
 __device__ __forceinline__ void warp_compact(unsigned long long* mybuf, int& cnt, float& tau, bool need) {
-    constexpr int E = (2 * KEEP) / 32;
+    constexpr int E = CAP / 32;
     unsigned mask = __ballot_sync(0xffffffffu, need);
     if (mask == 0) return;
     __syncwarp();
@@ -171,6 +171,10 @@ __device__ __forceinline__ void warp_compact(unsigned long long* mybuf, int& cnt
 // =====================================================================================================
 // (1) tcgen05 coarse scan
 // =====================================================================================================
+// list slots per (CTA, query): a compaction leaves KEEP entries and is triggered above CAP - 32, so the
+// capacity must leave real headroom (KEEP = 32 with 64 slots would compact after every single insert)
+__host__ __device__ constexpr int scan_cap(int keep) { return keep < 64 ? 128 : 2 * keep; }
+
 constexpr int kScanQ = 128;        // queries per launch = MMA M = TMEM lanes
 constexpr int kScanACols = 384;    // TMEM columns reserved for the query block (max dim of this path)
 constexpr int kScanThreads = 192;  // warp 0 TMA, warp 1 MMA + TMEM alloc, warps 2..5 epilogue
@@ -199,7 +203,7 @@ struct ScanParams {
 template <int BN, int NBUF, int NSLAB, int KD, bool TMA3D, int KEEP>
 __global__ void __launch_bounds__(kScanThreads, 1)
 scan_tf32_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
-    constexpr int CAP = 2 * KEEP;
+    constexpr int CAP = scan_cap(KEEP);
     constexpr int SLAB_BYTES = BN * 128 * KD;
     constexpr uint32_t IDESC = umma_idesc(2 /*tf32*/, 128, BN);
     static_assert(BN * NBUF <= 512 - kScanACols, "accumulators must fit beside the query block in TMEM");
@@ -375,7 +379,7 @@ scan_tf32_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
                         }
                     }
                 }
-                warp_compact<KEEP>(mybuf, cnt, tau, cnt > CAP - 32);
+                warp_compact<KEEP, CAP>(mybuf, cnt, tau, cnt > CAP - 32);
             }
             if (p.ablate & 4) {
                 tc_fence_before();
@@ -383,7 +387,7 @@ scan_tf32_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
             }
         }
         // final: every list sorted descending, zero padded to KEEP entries
-        warp_compact<KEEP>(mybuf, cnt, tau, true);
+        warp_compact<KEEP, CAP>(mybuf, cnt, tau, true);
         for (int e = cnt; e < KEEP; ++e) mybuf[e] = 0ull;
     }
 
@@ -1077,11 +1081,11 @@ int rmu_index_search(rmu_index* idx, const float* queries, int nq, int k, int64_
             sp.lists = d_scan;
             { static const char* ab = getenv("RMU_SCAN_ABLATE"); sp.ablate = ab ? atoi(ab) : 0; }
             const int grid = std::min(grid_scan, ntiles);
-            // threshold exchange (big corpora): a cheap lead pass (first ~2 % of every CTA's tiles, KEEP = 32)
+            // threshold exchange (big corpora): a cheap lead pass (first ~1 % of every CTA's tiles, KEEP = 32)
             // estimates per-query thresholds, then the full pass starts from them, so its epilogue almost
             // never takes the insert path.  The lead rows are read twice (+2 % traffic).
             static const int lead_env = [] { const char* e = getenv("RMU_SCAN_LEAD_PCT"); return e ? atoi(e) : -1; }();
-            const int lead_pct = lead_env >= 0 ? lead_env : 2;
+            const int lead_pct = lead_env >= 0 ? lead_env : 1;
             const int tiles_per_cta = ntiles / grid;
             constexpr int kLeadKeep = 32;
             const bool exchange = lead_pct > 0 && tiles_per_cta >= 16 && grid * kLeadKeep >= keep;
@@ -1092,7 +1096,7 @@ int rmu_index_search(rmu_index* idx, const float* queries, int nq, int k, int64_
                 rc = dispatch_scan(kLeadKeep, idx->tmap, sp, grid, st);
                 if (rc != RMU_OK) return rc;
                 { ProfScope _ps(PROF_FINALIZE, st);
-                select_tau_kernel<<<sp.nq, 256, 0, st>>>(d_scan, grid, 2 * kLeadKeep, kLeadKeep, keep, q0, d_tau0); }
+                select_tau_kernel<<<sp.nq, 256, 0, st>>>(d_scan, grid, scan_cap(kLeadKeep), kLeadKeep, keep, q0, d_tau0); }
                 count_launch();
                 RMU_CHECK_LAUNCH();
                 sp.phase = 2;

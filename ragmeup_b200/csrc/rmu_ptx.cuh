@@ -180,6 +180,18 @@ __device__ __forceinline__ uint64_t umma_desc_sw128_kmajor(uint32_t smem_addr) {
     return d;
 }
 
+// Same for rows of 64 bytes stored with the 64-byte swizzle (TMA box {64 B, rows}, SWIZZLE_64B):
+// 8-row groups are 512 B apart, layout type 4 = SWIZZLE_64B.
+__device__ __forceinline__ uint64_t umma_desc_sw64_kmajor(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFF);
+    d |= static_cast<uint64_t>(1) << 16;
+    d |= static_cast<uint64_t>(512 >> 4) << 32;
+    d |= static_cast<uint64_t>(1) << 46;
+    d |= static_cast<uint64_t>(4) << 61;
+    return d;
+}
+
 // Instruction descriptor (kind::tf32 / kind::f16): fp32 accumulate, both operands K-major.
 //   fmt: 0 = f16, 1 = bf16, 2 = tf32
 __host__ __device__ constexpr uint32_t umma_idesc(int fmt, int M, int N) {
