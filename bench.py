@@ -189,24 +189,38 @@ def run_gpu(args):
         order = torch.sort(logits.view(Q, R), dim=1, descending=True, stable=True).indices[:, :TOPN]
         return torch.gather(ids, 1, order), torch.gather(logits.view(Q, R), 1, order)
 
-    pair_typ_full_h = np.tile(PAIR_TYPES, npairs)
-    pair_cu_full_h = (np.arange(npairs + 1) * PAIR_LEN).astype(np.int32)
-
     host_t = {"embed": 0.0, "search": 0.0, "assemble": 0.0, "classify": 0.0, "select": 0.0}
+    my_typ_h = np.tile(PAIR_TYPES, p1 - p0)
+    my_cu_h = (np.arange(p1 - p0 + 1) * PAIR_LEN).astype(np.int32)
 
     def step_host():
-        """the same step through the host-buffer C-ABI entry points (N = 1 path of the plugin API)"""
+        """the same step through the HOST-buffer C-ABI entry points: token ids, vectors, candidates and
+        logits cross PCIe in both directions inside the call.  For N > 1 every rank searches its shard with
+        rmu_index_search_host and the per-shard candidates / logits are exchanged with the same collectives."""
         t = time.perf_counter()
         q_emb = emb.embed_host(q_ids_h, q_typ_h, q_cu_h, "mean", True)
         t1 = time.perf_counter(); host_t["embed"] += t1 - t
-        _, ids = index.search_host(q_emb, R)
+        sc, ids = index.search_host(q_emb, R, id_offset=sh.offset)
+        if world > 1:
+            s_d, i_d = torch.from_numpy(sc).to(dev), torch.from_numpy(ids).to(dev)
+            gs = [torch.empty_like(s_d) for _ in range(world)]
+            gi = [torch.empty_like(i_d) for _ in range(world)]
+            dist.all_gather(gs, s_d)
+            dist.all_gather(gi, i_d)
+            _, i_m = sh.merge_fn(torch.stack(gs), torch.stack(gi), index.metric)
+            ids = i_m.cpu().numpy()
         t2 = time.perf_counter(); host_t["search"] += t2 - t1
         docs = doc_tab_h[ids % DOC_TABLE]
         pairs = np.concatenate([np.full((Q, R, 1), 101, np.int32), np.broadcast_to(q_tok_h[:, None, :], (Q, R, Q_TOK)),
                                 np.full((Q, R, 1), 102, np.int32), docs, np.full((Q, R, 1), 102, np.int32)], 2)
-        flat = np.ascontiguousarray(pairs.reshape(-1))
+        flat = np.ascontiguousarray(pairs.reshape(npairs, PAIR_LEN)[p0:p1].reshape(-1))
         t3 = time.perf_counter(); host_t["assemble"] += t3 - t2
-        logits = ce.classify_host(flat, pair_typ_full_h, pair_cu_full_h)[:, 0]
+        logits = ce.classify_host(flat, my_typ_h, my_cu_h)[:, 0]
+        if world > 1:
+            l_d = torch.from_numpy(logits).to(dev)
+            parts = [torch.empty_like(l_d) for _ in range(world)]
+            dist.all_gather(parts, l_d)
+            logits = torch.cat(parts).cpu().numpy()
         t4 = time.perf_counter(); host_t["classify"] += t4 - t3
         order = np.argsort(-logits.reshape(Q, R), axis=1, kind="stable")[:, :TOPN]
         out = np.take_along_axis(ids, order, 1), np.take_along_axis(logits.reshape(Q, R), order, 1)
@@ -243,27 +257,32 @@ def run_gpu(args):
     prof = _lib.profile_read()
     launches = _lib.launch_count() - launches0
 
-    # ---------------- e2e through host buffers (rank 0's shard only when N > 1: the host API is per GPU)
-    e2e = None
-    if world == 1:
-        for _ in range(max(1, min(args.warmup, 2))):
-            h_ids, h_scores = step_host()
-        torch.cuda.synchronize()
-        for k_ in host_t:
-            host_t[k_] = 0.0
-        t0 = time.perf_counter()
-        n_e2e = max(1, min(args.steps, 5))
-        for _ in range(n_e2e):
-            h_ids, h_scores = step_host()
-        torch.cuda.synchronize()
-        e2e_ms = (time.perf_counter() - t0) * 1e3 / n_e2e
-        same = bool((h_ids == out_ids.cpu().numpy()).all())
-        h2d = q_ids_h.nbytes * 2 + q_cu_h.nbytes + Q * DIM * 4 + npairs * PAIR_LEN * 4 * 2 + pair_cu_full_h.nbytes
-        d2h = Q * DIM * 4 + Q * R * 12 + npairs * 4
-        e2e = {"value": Q / (e2e_ms * 1e-3), "unit": "queries/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(h2d),
-               "d2h_bytes_per_step": int(d2h), "ids_equal_device_path": same,
-               "host_ms_per_step": {k_: round(v_ * 1e3 / n_e2e, 2) for k_, v_ in host_t.items()},
-               "api": "rmu_encoder_embed_host + rmu_index_search_host + rmu_encoder_classify_host"}
+    # ---------------- e2e through host buffers (every rank runs its part; max over ranks)
+    for _ in range(max(1, min(args.warmup, 2))):
+        h_ids, h_scores = step_host()
+    barrier()
+    for k_ in host_t:
+        host_t[k_] = 0.0
+    t0 = time.perf_counter()
+    n_e2e = max(1, min(args.steps, 5))
+    for _ in range(n_e2e):
+        h_ids, h_scores = step_host()
+    torch.cuda.synchronize()
+    e2e_t = torch.tensor([(time.perf_counter() - t0) * 1e3 / n_e2e], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(e2e_t.item())
+    same = bool((h_ids == out_ids.cpu().numpy()).all())
+    my_pairs = p1 - p0
+    h2d = q_ids_h.nbytes * 2 + q_cu_h.nbytes + Q * DIM * 4 + my_pairs * PAIR_LEN * 4 * 2 + my_cu_h.nbytes
+    d2h = Q * DIM * 4 + Q * R * 12 + my_pairs * 4
+    if world > 1:
+        h2d += Q * R * 12 + my_pairs * 4
+        d2h += Q * R * 8 + npairs * 4
+    e2e = {"value": Q / (e2e_ms * 1e-3), "unit": "queries/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(h2d),
+           "d2h_bytes_per_step": int(d2h), "bytes_are": "per rank", "ids_equal_device_path": same,
+           "host_ms_per_step": {k_: round(v_ * 1e3 / n_e2e, 2) for k_, v_ in host_t.items()},
+           "api": "rmu_encoder_embed_host + rmu_index_search_host + rmu_encoder_classify_host"}
 
     if rank != 0:
         if world > 1:

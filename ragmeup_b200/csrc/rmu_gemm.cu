@@ -1,3 +1,4 @@
+#include <algorithm>
 #include <cstdlib>
 
 #include "rmu_gemm.cuh"
@@ -15,6 +16,14 @@ int make_split_operand(SplitOperand* op, __half* hi, __half* lo, int64_t rows, i
     if (rc == RMU_OK) rc = make_tmap_2d(&op->map64_lo, lo, static_cast<uint64_t>(rows), static_cast<uint64_t>(cols), pitch, 32, op->box64_rows, 2);
     if (rc == RMU_OK) rc = make_tmap_2d(&op->mapw_hi, hi, static_cast<uint64_t>(rows), static_cast<uint64_t>(cols), pitch, 64, op->box64_rows, 2);
     if (rc == RMU_OK) rc = make_tmap_2d(&op->mapw_lo, lo, static_cast<uint64_t>(rows), static_cast<uint64_t>(cols), pitch, 64, op->box64_rows, 2);
+    if (!is_activation) {
+        if (rc == RMU_OK) rc = make_tmap_2d(&op->map192_hi, hi, static_cast<uint64_t>(rows), static_cast<uint64_t>(cols), pitch, 64, 192, 2);
+        if (rc == RMU_OK) rc = make_tmap_2d(&op->map192_lo, lo, static_cast<uint64_t>(rows), static_cast<uint64_t>(cols), pitch, 64, 192, 2);
+        if (rc == RMU_OK) rc = make_tmap_2d(&op->map256_hi, hi, static_cast<uint64_t>(rows), static_cast<uint64_t>(cols), pitch, 64, 256, 2);
+        if (rc == RMU_OK) rc = make_tmap_2d(&op->map256_lo, lo, static_cast<uint64_t>(rows), static_cast<uint64_t>(cols), pitch, 64, 256, 2);
+        if (rc == RMU_OK) rc = make_tmap_2d(&op->map96_hi, hi, static_cast<uint64_t>(rows), static_cast<uint64_t>(cols), pitch, 64, 96, 2);
+        if (rc == RMU_OK) rc = make_tmap_2d(&op->map96_lo, lo, static_cast<uint64_t>(rows), static_cast<uint64_t>(cols), pitch, 64, 96, 2);
+    }
     return rc;
 }
 
@@ -41,26 +50,61 @@ static int launch_wide(const SplitOperand& A, const SplitOperand& W, const GemmP
     return RMU_OK;
 }
 
-template <int MODE>
-static int launch_mode(const SplitOperand& A, const SplitOperand& W, const GemmParams& p, int sms, cudaStream_t st) {
-    auto kern = gemm_f16x3_kernel<MODE>;
+template <int MODE, int BN>
+static int launch_bn(const SplitOperand& A, const SplitOperand& W, const GemmParams& p, int sms, cudaStream_t st) {
+    auto kern = gemm_f16x3_kernel<MODE, BN>;
     static bool attr_set = false;
     if (!attr_set) {
         RMU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kGemmSmem)));
         attr_set = true;
     }
-    const int tiles = ((p.M + kGemmBM - 1) / kGemmBM) * (p.N / kGemmBN);
+    const int tiles = ((p.M + kGemmBM - 1) / kGemmBM) * (p.N / BN);
     const int grid = tiles < sms ? tiles : sms;
     ProfScope _ps(PROF_GEMM, st);
-    kern<<<grid, kGemmThreads, kGemmSmem, st>>>(A.map_hi, A.map_lo, W.map_hi, W.map_lo, p);
+    const CUtensorMap& wh = BN == 128 ? W.map_hi : BN == 192 ? W.map192_hi : W.map256_hi;
+    const CUtensorMap& wl = BN == 128 ? W.map_lo : BN == 192 ? W.map192_lo : W.map256_lo;
+    kern<<<grid, kGemmThreads, kGemmSmem, st>>>(A.map_hi, A.map_lo, wh, wl, p);
     count_launch();
     RMU_CHECK_LAUNCH();
     return RMU_OK;
 }
 
+template <int MODE>
+static int launch_pair(const SplitOperand& A, const SplitOperand& W, const GemmParams& p, int sms, cudaStream_t st) {
+    auto kern = gemm_f16x3_pair_kernel<MODE>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        RMU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kPairSmem)));
+        attr_set = true;
+    }
+    const int tiles = ((p.M + 255) / 256) * (p.N / kPairBN);
+    int grid = 2 * std::min(tiles, sms / 2);          // whole CTA pairs
+    ProfScope _ps(PROF_GEMM, st);
+    kern<<<grid, kGemmThreads, kPairSmem, st>>>(A.map_hi, A.map_lo, W.map96_hi, W.map96_lo, p);
+    count_launch();
+    RMU_CHECK_LAUNCH();
+    return RMU_OK;
+}
+
+// tile width: RMU_GEMM_BN = 128 | 192 | 256 forces one (when it divides N); default 192, else 256, else 128
+template <int MODE>
+static int launch_mode(const SplitOperand& A, const SplitOperand& W, const GemmParams& p, int sms, cudaStream_t st) {
+    static const int pair = [] { const char* e = getenv("RMU_GEMM_PAIR"); return e ? atoi(e) : 0; }();
+    if (pair && p.N % kPairBN == 0 && W.box64_rows == kWideBN) return launch_pair<MODE>(A, W, p, sms, st);
+    static const int force = [] { const char* e = getenv("RMU_GEMM_BN"); return e ? atoi(e) : 0; }();
+    int bn = 128;
+    if (force == 128 || force == 192 || force == 256) { if (p.N % force == 0) bn = force; }
+    else if (p.N % 192 == 0) bn = 192;      // measured best on the MiniLM / bge shapes (768, 1152, 1536, 2304, 3072 ...)
+    else if (p.N % 256 == 0) bn = 256;
+    if (W.box64_rows != kWideBN) bn = 128;   // operand without the wide weight maps
+    if (bn == 256) return launch_bn<MODE, 256>(A, W, p, sms, st);
+    if (bn == 192) return launch_bn<MODE, 192>(A, W, p, sms, st);
+    return launch_bn<MODE, 128>(A, W, p, sms, st);
+}
+
 int launch_gemm(int mode, const SplitOperand& A, const SplitOperand& W, const GemmParams& p, int sms, cudaStream_t st) {
     if (p.M <= 0) return RMU_OK;
-    if (p.N % kGemmBN != 0 || p.K % kGemmBK != 0 || A.cols != p.K || W.cols != p.K || W.rows < p.N || A.rows < p.M) {
+    if (p.N % 128 != 0 || p.K % kGemmBK != 0 || A.cols != p.K || W.cols != p.K || W.rows < p.N || A.rows < p.M) {
         set_error("launch_gemm: shape not supported (N % 128, K % 64)");
         return RMU_ERR_UNSUPPORTED;
     }

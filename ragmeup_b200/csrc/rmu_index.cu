@@ -63,6 +63,59 @@ __device__ __forceinline__ float exact_metric(const float* __restrict__ q, const
     return den > 0.f ? ip / den : 0.f;
 }
 
+// The same arithmetic as exact_metric (same four fmaf chains per (query,row), so bit-identical results)
+// for QT queries at once: the row is read once for all of them.
+template <int QT>
+__device__ __forceinline__ void exact_metric_multi(const float* __restrict__ qs /*[QT][D]*/, const float* __restrict__ x,
+                                                   int D, int metric, const float* __restrict__ qnorm, float (&out)[QT]) {
+    float a[QT][4];
+#pragma unroll
+    for (int i = 0; i < QT; ++i) a[i][0] = a[i][1] = a[i][2] = a[i][3] = 0.f;
+    float n0 = 0.f, n1 = 0.f, n2 = 0.f, n3 = 0.f;
+    const int D4 = D & ~3;
+    if (metric == RMU_METRIC_L2) {
+        for (int d = 0; d < D4; d += 4) {
+            const float x0 = x[d], x1 = x[d + 1], x2 = x[d + 2], x3 = x[d + 3];
+#pragma unroll
+            for (int i = 0; i < QT; ++i) {
+                const float* q = qs + i * D;
+                const float e0 = q[d] - x0, e1 = q[d + 1] - x1, e2 = q[d + 2] - x2, e3 = q[d + 3] - x3;
+                a[i][0] = fmaf(e0, e0, a[i][0]); a[i][1] = fmaf(e1, e1, a[i][1]);
+                a[i][2] = fmaf(e2, e2, a[i][2]); a[i][3] = fmaf(e3, e3, a[i][3]);
+            }
+        }
+        for (int d = D4; d < D; ++d) {
+#pragma unroll
+            for (int i = 0; i < QT; ++i) { const float e = qs[i * D + d] - x[d]; a[i][0] = fmaf(e, e, a[i][0]); }
+        }
+#pragma unroll
+        for (int i = 0; i < QT; ++i) out[i] = (a[i][0] + a[i][1]) + (a[i][2] + a[i][3]);
+        return;
+    }
+    for (int d = 0; d < D4; d += 4) {
+        const float x0 = x[d], x1 = x[d + 1], x2 = x[d + 2], x3 = x[d + 3];
+        if (metric == RMU_METRIC_COSINE) { n0 = fmaf(x0, x0, n0); n1 = fmaf(x1, x1, n1); n2 = fmaf(x2, x2, n2); n3 = fmaf(x3, x3, n3); }
+#pragma unroll
+        for (int i = 0; i < QT; ++i) {
+            const float* q = qs + i * D;
+            a[i][0] = fmaf(q[d], x0, a[i][0]); a[i][1] = fmaf(q[d + 1], x1, a[i][1]);
+            a[i][2] = fmaf(q[d + 2], x2, a[i][2]); a[i][3] = fmaf(q[d + 3], x3, a[i][3]);
+        }
+    }
+    for (int d = D4; d < D; ++d) {
+        if (metric == RMU_METRIC_COSINE) n0 = fmaf(x[d], x[d], n0);
+#pragma unroll
+        for (int i = 0; i < QT; ++i) a[i][0] = fmaf(qs[i * D + d], x[d], a[i][0]);
+    }
+    const float xn = sqrtf((n0 + n1) + (n2 + n3));
+#pragma unroll
+    for (int i = 0; i < QT; ++i) {
+        const float ip = (a[i][0] + a[i][1]) + (a[i][2] + a[i][3]);
+        if (metric == RMU_METRIC_IP) out[i] = ip;
+        else { const float den = qnorm[i] * xn; out[i] = den > 0.f ? ip / den : 0.f; }
+    }
+}
+
 // "larger is better" key of a metric value
 __device__ __forceinline__ float metric_to_rank(float v, int metric) { return metric == RMU_METRIC_L2 ? -v : v; }
 
@@ -429,34 +482,58 @@ struct ExactParams {
     int keep;                  // pow2 <= kChunk
 };
 
+constexpr int kExactQT = 8;    // queries scored per pass over a chunk of rows
+
 __global__ void __launch_bounds__(256) exact_scan_kernel(const ExactParams p) {
     __shared__ unsigned long long keys[kChunk];
     __shared__ float red[32];
-    extern __shared__ float qs[];  // [dim]
+    __shared__ float qn[kExactQT];
+    extern __shared__ float esm[];                 // qs [QT][dim], then sc [QT][kChunk]
+    float* qs = esm;
+    float* sc = esm + kExactQT * p.dim;
     const int nsel = p.nsel ? *p.nsel : p.nq_total;
     const long long row0 = static_cast<long long>(blockIdx.x) * kChunk;
-    for (int f = blockIdx.y; f < nsel; f += gridDim.y) {
-        const int qg = p.qmap ? p.qmap[f] : f;
+    const int ngroups = (nsel + kExactQT - 1) / kExactQT;
+    for (int grp = blockIdx.y; grp < ngroups; grp += gridDim.y) {
+        const int f0 = grp * kExactQT;
+        const int nq = min(kExactQT, nsel - f0);
         __syncthreads();
-        float part = 0.f;
-        for (int d = threadIdx.x; d < p.dim; d += blockDim.x) {
-            float v = p.q[static_cast<long long>(qg) * p.dim + d];
-            qs[d] = v;
-            part = fmaf(v, v, part);
+        for (int i = 0; i < kExactQT; ++i) {
+            float part = 0.f;
+            if (i < nq) {
+                const int qg = p.qmap ? p.qmap[f0 + i] : f0 + i;
+                for (int d = threadIdx.x; d < p.dim; d += blockDim.x) {
+                    const float v = p.q[static_cast<long long>(qg) * p.dim + d];
+                    qs[i * p.dim + d] = v;
+                    part = fmaf(v, v, part);
+                }
+            } else {
+                for (int d = threadIdx.x; d < p.dim; d += blockDim.x) qs[i * p.dim + d] = 0.f;
+            }
+            const float nrm = sqrtf(block_sum(part, red));
+            if (threadIdx.x == 0) qn[i] = nrm;
         }
-        const float qnorm = sqrtf(block_sum(part, red));
+        __syncthreads();
         for (int r = threadIdx.x; r < kChunk; r += blockDim.x) {
             const long long row = row0 + r;
-            unsigned long long key = 0ull;
             if (row < p.n) {
-                float v = exact_metric(qs, p.x + row * p.dim, p.dim, p.metric, qnorm);
-                key = make_key(metric_to_rank(v, p.metric), static_cast<uint32_t>(row));
+                float v[kExactQT];
+                exact_metric_multi<kExactQT>(qs, p.x + row * p.dim, p.dim, p.metric, qn, v);
+#pragma unroll
+                for (int i = 0; i < kExactQT; ++i) sc[i * kChunk + r] = v[i];
             }
-            keys[r] = key;
         }
-        block_bitonic_desc(keys, kChunk);
-        unsigned long long* out = p.lists + (static_cast<long long>(blockIdx.x) * p.nq_total + f) * p.keep;
-        for (int e = threadIdx.x; e < p.keep; e += blockDim.x) out[e] = keys[e];
+        __syncthreads();
+        for (int i = 0; i < nq; ++i) {
+            for (int r = threadIdx.x; r < kChunk; r += blockDim.x) {
+                const long long row = row0 + r;
+                keys[r] = row < p.n ? make_key(metric_to_rank(sc[i * kChunk + r], p.metric), static_cast<uint32_t>(row)) : 0ull;
+            }
+            block_bitonic_desc(keys, kChunk);
+            unsigned long long* out = p.lists + (static_cast<long long>(blockIdx.x) * p.nq_total + f0 + i) * p.keep;
+            for (int e = threadIdx.x; e < p.keep; e += blockDim.x) out[e] = keys[e];
+            __syncthreads();
+        }
     }
 }
 
@@ -829,8 +906,11 @@ struct rmu_index {
     // scratch
     void* ws = nullptr;
     size_t ws_bytes = 0;
+    void* hbuf = nullptr;          // device staging of the *_host entry points (queries, scores, ids)
+    size_t hbuf_bytes = 0;
     cudaEvent_t ws_done = nullptr;
     std::mutex mu;
+    std::mutex host_mu;            // serialises the *_host entry points (they share hbuf and synchronise anyway)
 };
 
 static int ensure_ws(rmu_index* idx, size_t bytes) {
@@ -936,7 +1016,7 @@ int rmu_index_create(int dim, int metric, rmu_index** out) {
 void rmu_index_destroy(rmu_index* idx) {
     if (!idx) return;
     cudaDeviceSynchronize();
-    cudaFree(idx->x); cudaFree(idx->rscale); cudaFree(idx->rbias); cudaFree(idx->max_norm_bits); cudaFree(idx->ws);
+    cudaFree(idx->x); cudaFree(idx->rscale); cudaFree(idx->rbias); cudaFree(idx->max_norm_bits); cudaFree(idx->ws); cudaFree(idx->hbuf);
     if (idx->ws_done) cudaEventDestroy(idx->ws_done);
     delete idx;
 }
@@ -1130,11 +1210,19 @@ int rmu_index_search(rmu_index* idx, const float* queries, int nq, int k, int64_
         ep.x = idx->x; ep.n = N; ep.dim = D; ep.metric = idx->metric; ep.q = queries;
         ep.qmap = tensor_ok ? d_qmap : nullptr; ep.nsel = tensor_ok ? d_nsel : nullptr; ep.nq_total = nq;
         ep.lists = d_exact; ep.keep = keepx;
-        int gy = tensor_ok ? 1 : std::min(nq, std::max(1, (2 * idx->sms + nchunks - 1) / nchunks));
+        const int ngroups = (nq + kExactQT - 1) / kExactQT;
+        int gy = tensor_ok ? 1 : std::min(ngroups, std::max(1, (2 * idx->sms + nchunks - 1) / nchunks));
         gy = std::min(gy, 65535);
         dim3 eg(static_cast<unsigned>(nchunks), static_cast<unsigned>(gy));
+        const size_t esmem = sizeof(float) * kExactQT * (static_cast<size_t>(D) + kChunk);
+        if (esmem > 200 * 1024) { set_error("rmu_index_search: dim too large for the exact scan"); return RMU_ERR_UNSUPPORTED; }
+        static size_t esmem_set = 0;
+        if (esmem > esmem_set) {
+            RMU_CUDA(cudaFuncSetAttribute(exact_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(esmem)));
+            esmem_set = esmem;
+        }
         { ProfScope _ps(PROF_EXACT, st);
-        exact_scan_kernel<<<eg, 256, qsmem, st>>>(ep); }
+        exact_scan_kernel<<<eg, 256, esmem, st>>>(ep); }
         count_launch();
         RMU_CHECK_LAUNCH();
         FinalizeParams fp{};
@@ -1191,18 +1279,32 @@ int rmu_index_search_host(rmu_index* idx, const float* queries_h, int nq, int k,
         return RMU_ERR_ARG;
     }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    float* dq = nullptr; float* ds = nullptr; int64_t* di = nullptr;
-    const size_t qb = static_cast<size_t>(nq) * idx->dim * sizeof(float);
-    RMU_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&dq), qb, st));
-    RMU_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&ds), static_cast<size_t>(nq) * k * sizeof(float), st));
-    RMU_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&di), static_cast<size_t>(nq) * k * sizeof(int64_t), st));
-    RMU_CUDA(cudaMemcpyAsync(dq, queries_h, qb, cudaMemcpyHostToDevice, st));
+    std::lock_guard<std::mutex> hg(idx->host_mu);
+    const size_t qb = (static_cast<size_t>(nq) * idx->dim * sizeof(float) + 255) & ~size_t(255);
+    const size_t sb = (static_cast<size_t>(nq) * k * sizeof(float) + 255) & ~size_t(255);
+    const size_t ib = static_cast<size_t>(nq) * k * sizeof(int64_t);
+    {
+        // handle-owned staging (a cudaMallocAsync/free pair per call costs milliseconds once the pool is trimmed)
+        std::lock_guard<std::mutex> g(idx->mu);
+        if (qb + sb + ib > idx->hbuf_bytes) {
+            RMU_CUDA(cudaStreamSynchronize(st));
+            if (idx->hbuf) RMU_CUDA(cudaFree(idx->hbuf));
+            idx->hbuf = nullptr;
+            idx->hbuf_bytes = 0;
+            RMU_CUDA(cudaMalloc(&idx->hbuf, 2 * (qb + sb + ib)));
+            idx->hbuf_bytes = 2 * (qb + sb + ib);
+        }
+    }
+    uint8_t* hb = static_cast<uint8_t*>(idx->hbuf);
+    float* dq = reinterpret_cast<float*>(hb);
+    float* ds = reinterpret_cast<float*>(hb + qb);
+    int64_t* di = reinterpret_cast<int64_t*>(hb + qb + sb);
+    RMU_CUDA(cudaMemcpyAsync(dq, queries_h, static_cast<size_t>(nq) * idx->dim * sizeof(float), cudaMemcpyHostToDevice, st));
     int rc = rmu_index_search(idx, dq, nq, k, id_offset, mode, ds, di, nullptr, st);
     if (rc == RMU_OK) {
         RMU_CUDA(cudaMemcpyAsync(out_scores_h, ds, static_cast<size_t>(nq) * k * sizeof(float), cudaMemcpyDeviceToHost, st));
-        RMU_CUDA(cudaMemcpyAsync(out_ids_h, di, static_cast<size_t>(nq) * k * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+        RMU_CUDA(cudaMemcpyAsync(out_ids_h, di, ib, cudaMemcpyDeviceToHost, st));
     }
-    cudaFreeAsync(dq, st); cudaFreeAsync(ds, st); cudaFreeAsync(di, st);
     RMU_CUDA(cudaStreamSynchronize(st));
     return rc;
 }
