@@ -14,7 +14,7 @@ from typing import Any, Dict, List, Optional, Sequence, Tuple
 import numpy as np
 
 from .embeddings import _check_device
-from .encoder import BertEncoder
+from .encoder import MAX_TOKENS_PER_CALL, BertEncoder
 from .tokenizer import encode_ragged, load_tokenizer
 from .weights import resolve_model
 
@@ -66,7 +66,7 @@ class HuggingFaceCrossEncoder(BaseCrossEncoder):
         b = [p[1].strip() for p in pairs]
         ids, typ, cu = encode_ragged(self.tokenizer, a, b, self.max_length)
         outs = []
-        for s, e in BertEncoder._chunks(cu, 32768):
+        for s, e in BertEncoder._chunks(cu, MAX_TOKENS_PER_CALL):
             t0, t1 = int(cu[s]), int(cu[e])
             sub_cu = (cu[s:e + 1] - cu[s]).astype(np.int32)
             outs.append(self.client.classify_tokens(ids[t0:t1], typ[t0:t1], sub_cu, int(np.max(np.diff(sub_cu)))))

@@ -434,6 +434,12 @@ __device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], const void* 
                  : "r"(smem_u32(smem_row)));
 }
 
+__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], const void* smem_row) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+                 : "r"(smem_u32(smem_row)));
+}
+
 constexpr int kAttWarps = 10;   // 160 query rows per CTA (a 147-token rerank pair fits one CTA)
 
 __device__ __forceinline__ float fast_exp2(float x) {   // ex2.approx: 2 ulp, exp2(-inf) = +0
@@ -520,14 +526,18 @@ __global__ void __launch_bounds__(kAttWarps * 32) attention_planes_kernel(const 
             const bool full_blk = kb0 + 32 <= nk16;      // else only the first two n-tiles hold keys
 #pragma unroll
             for (int ks = 0; ks < KS; ++ks) {
+                // K fragments of four key tiles through two ldmatrix.x4 per plane: matrices (keys a, d lo),
+                // (keys a, d hi), (keys a+1, d lo), (keys a+1, d hi); rows past nk16 are stale smem, masked below
                 uint32_t bh[4][2], bl[4][2];
+                const int lrow = (lane & 7) + ((lane >> 4) << 3);
+                const int lcol = ks * 16 + ((lane >> 3) & 1) * 8;
 #pragma unroll
-                for (int n = 0; n < 4; ++n) {
-                    const int key = kb0 + n * 8 + g;     // rows past nk16 are stale smem, masked below
-                    bh[n][0] = *reinterpret_cast<const uint32_t*>(Kh + key * KSTR + ks * 16 + 2 * t);
-                    bh[n][1] = *reinterpret_cast<const uint32_t*>(Kh + key * KSTR + ks * 16 + 2 * t + 8);
-                    bl[n][0] = *reinterpret_cast<const uint32_t*>(Kl + key * KSTR + ks * 16 + 2 * t);
-                    bl[n][1] = *reinterpret_cast<const uint32_t*>(Kl + key * KSTR + ks * 16 + 2 * t + 8);
+                for (int n2 = 0; n2 < 2; ++n2) {
+                    uint32_t th[4], tl[4];
+                    ldmatrix_x4(th, Kh + (kb0 + n2 * 16 + lrow) * KSTR + lcol);
+                    ldmatrix_x4(tl, Kl + (kb0 + n2 * 16 + lrow) * KSTR + lcol);
+                    bh[2 * n2][0] = th[0]; bh[2 * n2][1] = th[1]; bh[2 * n2 + 1][0] = th[2]; bh[2 * n2 + 1][1] = th[3];
+                    bl[2 * n2][0] = tl[0]; bl[2 * n2][1] = tl[1]; bl[2 * n2 + 1][0] = tl[2]; bl[2 * n2 + 1][1] = tl[3];
                 }
 #pragma unroll
                 for (int n = 0; n < 4; ++n) if (n < 2 || full_blk) mma16816(sacc[n], qh[ks], bh[n]);
@@ -537,11 +547,16 @@ __global__ void __launch_bounds__(kAttWarps * 32) attention_planes_kernel(const 
                 for (int n = 0; n < 4; ++n) if (n < 2 || full_blk) mma16816(sacc[n], qh[ks], bl[n]);
             }
             float bm0 = -INFINITY, bm1 = -INFINITY;
+            if (kb0 + 32 > nk) {                     // only the last key block holds keys past the sequence end
+#pragma unroll
+                for (int n = 0; n < 4; ++n) {
+                    const int k0 = kb0 + n * 8 + 2 * t;
+                    if (k0 >= nk) { sacc[n][0] = -INFINITY; sacc[n][2] = -INFINITY; }
+                    if (k0 + 1 >= nk) { sacc[n][1] = -INFINITY; sacc[n][3] = -INFINITY; }
+                }
+            }
 #pragma unroll
             for (int n = 0; n < 4; ++n) {
-                const int k0 = kb0 + n * 8 + 2 * t;
-                if (k0 >= nk) { sacc[n][0] = -INFINITY; sacc[n][2] = -INFINITY; }
-                if (k0 + 1 >= nk) { sacc[n][1] = -INFINITY; sacc[n][3] = -INFINITY; }
                 bm0 = fmaxf(bm0, fmaxf(sacc[n][0], sacc[n][1]));
                 bm1 = fmaxf(bm1, fmaxf(sacc[n][2], sacc[n][3]));
             }

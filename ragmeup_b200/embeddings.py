@@ -19,7 +19,7 @@ from typing import Any, Dict, List, Optional
 import numpy as np
 
 from . import _lib
-from .encoder import BertEncoder
+from .encoder import MAX_TOKENS_PER_CALL, BertEncoder
 from .tokenizer import encode_ragged, load_tokenizer
 from .weights import resolve_model
 
@@ -66,7 +66,7 @@ class HuggingFaceEmbeddings:
         texts = [t.replace("\n", " ").strip() for t in texts]
         ids, typ, cu = encode_ragged(self.tokenizer, texts, None, self.max_seq_length)
         outs = []
-        for s, e in BertEncoder._chunks(cu, 32768):
+        for s, e in BertEncoder._chunks(cu, MAX_TOKENS_PER_CALL):
             t0, t1 = int(cu[s]), int(cu[e])
             sub_cu = (cu[s:e + 1] - cu[s]).astype(np.int32)
             outs.append(self.client.embed_tokens(ids[t0:t1], typ[t0:t1], sub_cu, int(np.max(np.diff(sub_cu))),

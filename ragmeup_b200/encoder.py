@@ -15,7 +15,7 @@ from . import _lib
 from .weights import BertConfig, weight_names
 
 POOL = {"mean": 0, "cls": 1}
-MAX_TOKENS_PER_CALL = 32768     # bounds the activation workspace (~17 KB/token for MiniLM shapes)
+MAX_TOKENS_PER_CALL = 131072    # bounds the activation workspace (~19 KB/token for MiniLM shapes => ~2.5 GB)
 
 
 class BertEncoder:

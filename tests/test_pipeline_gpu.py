@@ -109,3 +109,36 @@ def test_rerank_matches_reference_semantics(stack, tmp_path):
     a = [d.metadata["pk"] for d in db.similarity_search(queries[2], k=5)]
     b = [d.metadata["pk"] for d in db2.similarity_search(queries[2], k=5)]
     assert a == b and len(db2) == 50
+
+
+def test_concurrent_callers_share_handles(stack):
+    """Flask serves /chat on several threads with ONE shared RAGHelper (server/server.py:141-146,394):
+    concurrent embed_query / search / score on the same handles must return the single-threaded answers."""
+    import threading
+    from ragmeup_b200.vectorstore import Milvus
+    emb, ce, docs, queries = stack
+    db = Milvus(emb, collection_name="t")
+    db.add_documents([Document(t, {"source": "s"}) for t in docs[:500]], ids=[f"k{i}" for i in range(500)])
+    want_docs = {q: [d.metadata["pk"] for d in db.similarity_search(q, k=5)] for q in queries[:6]}
+    pairs = [(queries[0], d) for d in docs[:12]]
+    want_scores = ce.score(pairs)
+    want_emb = np.asarray(emb.embed_query(queries[1]))
+    errors = []
+
+    def worker(tid):
+        try:
+            for it in range(6):
+                q = queries[(tid + it) % 6]
+                got = [d.metadata["pk"] for d in db.similarity_search(q, k=5)]
+                assert got == want_docs[q]
+                assert np.abs(ce.score(pairs) - want_scores).max() < 1e-6
+                assert np.abs(np.asarray(emb.embed_query(queries[1])) - want_emb).max() < 1e-6
+        except Exception as e:  # noqa: BLE001
+            errors.append(repr(e))
+
+    threads = [threading.Thread(target=worker, args=(t,)) for t in range(4)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
