@@ -78,8 +78,13 @@ def lib() -> C.CDLL:
         if _lib is not None:
             return _lib
         if not os.path.exists(LIB_PATH):
-            raise RmuError(f"{LIB_PATH} is not built: run `python -m ragmeup_b200.build` "
-                           f"(there is no CPU fallback for this path)")
+            # the library is built in-tree and normally travels with the checkout; build it when absent
+            try:
+                from . import build as _build
+                _build.build()
+            except Exception as e:  # noqa: BLE001
+                raise RmuError(f"{LIB_PATH} is not built and building it failed ({e}): run "
+                               f"`python -m ragmeup_b200.build` (there is no CPU fallback for this path)") from e
         l = C.CDLL(LIB_PATH)
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(l, name)
@@ -113,7 +118,8 @@ def stream_ptr(torch_stream=None) -> int:
     return int(s.cuda_stream)
 
 
-PROF_CLASSES = ["scan", "finalize", "exact", "merge", "gemm", "attention", "layernorm", "embedding", "pool_head", "misc"]
+PROF_CLASSES = ["scan", "finalize", "exact", "merge", "gemm", "attention", "layernorm", "embedding", "pool_head", "misc",
+                "scan_lead"]
 
 
 def profile_enable(on: bool) -> None:

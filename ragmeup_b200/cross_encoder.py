@@ -15,7 +15,7 @@ import numpy as np
 
 from .embeddings import _check_device
 from .encoder import MAX_TOKENS_PER_CALL, BertEncoder
-from .tokenizer import encode_ragged, load_tokenizer
+from .tokenizer import RaggedTokenizer, load_tokenizer
 from .weights import resolve_model
 
 
@@ -38,6 +38,7 @@ class HuggingFaceCrossEncoder(BaseCrossEncoder):
         self.max_length = min(int(max_len), cfg.max_pos)
         self.activation = activation
         self.tokenizer = load_tokenizer(vocab_src, cfg.vocab_size)
+        self._ragged = RaggedTokenizer(self.tokenizer, self.max_length)
         self.client = BertEncoder(cfg, w, with_head=True, device=device)
 
     def _post(self, logits: np.ndarray) -> np.ndarray:
@@ -53,7 +54,7 @@ class HuggingFaceCrossEncoder(BaseCrossEncoder):
             raise IndexError("score() received no text pairs")
         a = [p[0].strip() for p in pairs]
         b = [p[1].strip() for p in pairs]
-        ids, typ, cu = encode_ragged(self.tokenizer, a, b, self.max_length)
+        ids, typ, cu = self._ragged(a, b)
         return self._post(self.client.classify_host(ids, typ, cu))
 
     def score_tensor(self, text_pairs: Sequence[Tuple[str, str]]):
@@ -64,7 +65,7 @@ class HuggingFaceCrossEncoder(BaseCrossEncoder):
             raise IndexError("score_tensor() received no text pairs")
         a = [p[0].strip() for p in pairs]
         b = [p[1].strip() for p in pairs]
-        ids, typ, cu = encode_ragged(self.tokenizer, a, b, self.max_length)
+        ids, typ, cu = self._ragged(a, b)
         outs = []
         for s, e in BertEncoder._chunks(cu, MAX_TOKENS_PER_CALL):
             t0, t1 = int(cu[s]), int(cu[e])

@@ -737,7 +737,9 @@ struct rmu_encoder {
     int *d_ids = nullptr, *d_typ = nullptr, *d_cu = nullptr;   // staging for the *_host entry points
     float* d_out = nullptr;
     size_t d_out_elems = 0;
+    cudaEvent_t ws_done = nullptr;   // last use of the shared activation workspace (callers on other streams wait on it)
     std::mutex mu;
+    std::mutex host_mu;   // the *_host entry points share the staging buffers above: one at a time per handle
 };
 
 template <typename T>
@@ -825,6 +827,7 @@ static int run_encoder(rmu_encoder* e, const int32_t* ids, const int32_t* type_i
     if (max_seqlen > c.max_pos) { set_error("sequence longer than max_position_embeddings"); return RMU_ERR_ARG; }
     int rc = ensure_tokens(e, T, B);
     if (rc != RMU_OK) return rc;
+    RMU_CUDA(cudaStreamWaitEvent(st, e->ws_done, 0));    // the activation workspace is shared by all callers
     const int wpb = 8;
     const unsigned tok_blocks = static_cast<unsigned>((T + wpb - 1) / wpb);
     { ProfScope _ps(PROF_EMBED, st);
@@ -930,7 +933,8 @@ int rmu_encoder_create(const rmu_bert_config* cfg, const float* const* w, int n_
     rmu_encoder* e = new rmu_encoder();
     e->cfg = *cfg;
     e->has_head = has_head;
-    if (cudaGetDevice(&e->device) != cudaSuccess || (e->sms = device_sm_count()) <= 0) {
+    if (cudaGetDevice(&e->device) != cudaSuccess || (e->sms = device_sm_count()) <= 0 ||
+        cudaEventCreateWithFlags(&e->ws_done, cudaEventDisableTiming) != cudaSuccess) {
         set_error("rmu_encoder_create: no CUDA device (this library has no CPU path)");
         delete e;
         return RMU_ERR_CUDA;
@@ -986,6 +990,7 @@ void rmu_encoder_destroy(rmu_encoder* e) {
     cudaDeviceSynchronize();
     free_acts(e);
     for (void* p : e->allocs) cudaFree(p);
+    if (e->ws_done) cudaEventDestroy(e->ws_done);
     delete e;
 }
 
@@ -1002,6 +1007,7 @@ int rmu_encoder_embed(rmu_encoder* e, const int32_t* ids, const int32_t* type_id
     pool_kernel<<<B, 256, 0, st>>>(e->X.hi, e->X.lo, cu, e->cfg.hidden, pool_mode, normalize, out);
     count_launch();
     RMU_CHECK_LAUNCH();
+    RMU_CUDA(cudaEventRecord(e->ws_done, st));
     return RMU_OK;
 }
 
@@ -1020,6 +1026,7 @@ int rmu_encoder_classify(rmu_encoder* e, const int32_t* ids, const int32_t* type
                                                             e->cw, e->cb, out);
     count_launch();
     RMU_CHECK_LAUNCH();
+    RMU_CUDA(cudaEventRecord(e->ws_done, st));
     return RMU_OK;
 }
 
@@ -1035,6 +1042,7 @@ int rmu_encoder_hidden(rmu_encoder* e, const int32_t* ids, const int32_t* type_i
     join_planes_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(e->X.hi, e->X.lo, out, n);
     count_launch();
     RMU_CHECK_LAUNCH();
+    RMU_CUDA(cudaEventRecord(e->ws_done, st));
     return RMU_OK;
 }
 
@@ -1056,6 +1064,7 @@ int rmu_encoder_embed_host(rmu_encoder* e, const int32_t* ids_h, const int32_t* 
     int rc = check_batch(e, ids_h, cu_h, B, T, out_h);
     if (rc != RMU_OK) return rc;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    std::lock_guard<std::mutex> hg(e->host_mu);
     rc = stage_batch(e, ids_h, typ_h, cu_h, B, T, st);
     if (rc != RMU_OK) return rc;
     rc = rmu_encoder_embed(e, e->d_ids, typ_h ? e->d_typ : nullptr, e->d_cu, B, T, max_seqlen, pool_mode, normalize, e->d_out, st);
@@ -1070,6 +1079,7 @@ int rmu_encoder_classify_host(rmu_encoder* e, const int32_t* ids_h, const int32_
     int rc = check_batch(e, ids_h, cu_h, B, T, out_h);
     if (rc != RMU_OK) return rc;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    std::lock_guard<std::mutex> hg(e->host_mu);
     rc = stage_batch(e, ids_h, typ_h, cu_h, B, T, st);
     if (rc != RMU_OK) return rc;
     rc = rmu_encoder_classify(e, e->d_ids, typ_h ? e->d_typ : nullptr, e->d_cu, B, T, max_seqlen, e->d_out, st);

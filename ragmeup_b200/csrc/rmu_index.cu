@@ -134,7 +134,8 @@ __device__ __forceinline__ float block_sum(float v, float* red /*[32]*/) {
 // per-row statistics at insert time: cosine scale 1/||x||, L2 bias -0.5||x||^2, running max ||x||
 // =====================================================================================================
 __global__ void row_stats_kernel(const float* __restrict__ x, long long row0, long long n, int D, int metric,
-                                 float* __restrict__ rscale, float* __restrict__ rbias, unsigned* __restrict__ max_norm_bits) {
+                                 float* __restrict__ rscale, float* __restrict__ rbias, unsigned* __restrict__ max_norm_bits,
+                                 unsigned* __restrict__ max_dev_bits) {
     int warps_per_block = blockDim.x >> 5;
     long long r = static_cast<long long>(blockIdx.x) * warps_per_block + (threadIdx.x >> 5);
     if (r >= n) return;
@@ -147,6 +148,7 @@ __global__ void row_stats_kernel(const float* __restrict__ x, long long row0, lo
         if (metric == RMU_METRIC_COSINE) rscale[row0 + r] = nrm > 0.f ? 1.f / nrm : 0.f;
         if (metric == RMU_METRIC_L2) rbias[row0 + r] = -0.5f * s;
         atomicMax(max_norm_bits, __float_as_uint(nrm));  // non-negative floats order like uints
+        atomicMax(max_dev_bits, __float_as_uint(fabsf(s - 1.0f)));   // how far from unit norm the corpus gets
     }
 }
 
@@ -609,6 +611,7 @@ struct FinalizeParams {
     const int* qmap;   // exact mode: blockIdx.x -> query through qmap
     const int* nsel;   // exact mode: number of valid blockIdx.x
     int exact;         // 1: lists hold exact keys, no certificate
+    int unit_rows;     // 1: every row has ||x||^2 = 1 +- 1e-6 and the coarse keys are plain inner products
     int k;
     long long id_offset;
     const unsigned* max_norm_bits;
@@ -708,9 +711,10 @@ __global__ void __launch_bounds__(256) finalize_kernel(const FinalizeParams p) {
             const float xmax = __uint_as_float(*p.max_norm_bits);
             if (p.metric == RMU_METRIC_IP) { kth_key = rk; scale = qnorm * xmax; }
             else if (p.metric == RMU_METRIC_COSINE) { kth_key = rk * qnorm; scale = qnorm; }
-            else { kth_key = 0.5f * (qnorm * qnorm + rk); scale = qnorm * xmax; }  // rk = -dist
+            else { kth_key = 0.5f * (qnorm * qnorm + rk) + (p.unit_rows ? 0.5f : 0.f); scale = qnorm * xmax; }  // rk = -dist
             const float bound = key_score(T);
-            const float eps = p.eps_rel * scale + 1e-6f * (1.f + fabsf(kth_key));
+            // unit_rows: cosine / L2 keys were scanned as inner products, exact to 1e-6 (||x||^2 = 1 +- 1e-6)
+            const float eps = p.eps_rel * scale + 1e-6f * (1.f + fabsf(kth_key)) + (p.unit_rows ? 4e-6f * (1.f + qnorm) : 0.f);
             if (!(bound + eps < kth_key)) flag = 1;
             if (ncand < p.k) flag = 1;
         }
@@ -899,7 +903,9 @@ struct rmu_index {
     float* x = nullptr;
     float* rscale = nullptr;
     float* rbias = nullptr;
-    unsigned* max_norm_bits = nullptr;
+    unsigned* max_norm_bits = nullptr;   // [0] max ||x||, [1] max | ||x||^2 - 1 |
+    float* dev_h = nullptr;              // pinned host copy of [1], refreshed after every insert
+    cudaEvent_t stats_ev = nullptr;
     CUtensorMap tmap{};
     int64_t tmap_rows = -1;
     int tmap_bn = 0;
@@ -945,7 +951,7 @@ static int launch_scan(const CUtensorMap& tmap, const ScanParams& p, int grid, c
         RMU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
         attr_set = true;
     }
-    ProfScope _ps(PROF_SCAN, st);
+    ProfScope _ps(p.phase == 1 ? PROF_SCAN_LEAD : PROF_SCAN, st);
     kern<<<grid, kScanThreads, smem, st>>>(tmap, p);
     count_launch();
     RMU_CHECK_LAUNCH();
@@ -1005,8 +1011,10 @@ int rmu_index_create(int dim, int metric, rmu_index** out) {
         delete idx;
         return RMU_ERR_CUDA;
     }
-    cudaError_t e = cudaMalloc(&idx->max_norm_bits, sizeof(unsigned));
-    if (e == cudaSuccess) e = cudaMemset(idx->max_norm_bits, 0, sizeof(unsigned));
+    cudaError_t e = cudaMalloc(&idx->max_norm_bits, 2 * sizeof(unsigned));
+    if (e == cudaSuccess) e = cudaMemset(idx->max_norm_bits, 0, 2 * sizeof(unsigned));
+    if (e == cudaSuccess) e = cudaMallocHost(&idx->dev_h, sizeof(float));
+    if (e == cudaSuccess) { *idx->dev_h = 0.f; e = cudaEventCreateWithFlags(&idx->stats_ev, cudaEventDisableTiming); }
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&idx->ws_done, cudaEventDisableTiming);
     if (e != cudaSuccess) { set_error(std::string("rmu_index_create: ") + cudaGetErrorString(e)); delete idx; return RMU_ERR_CUDA; }
     *out = idx;
@@ -1018,6 +1026,8 @@ void rmu_index_destroy(rmu_index* idx) {
     cudaDeviceSynchronize();
     cudaFree(idx->x); cudaFree(idx->rscale); cudaFree(idx->rbias); cudaFree(idx->max_norm_bits); cudaFree(idx->ws); cudaFree(idx->hbuf);
     if (idx->ws_done) cudaEventDestroy(idx->ws_done);
+    if (idx->stats_ev) cudaEventDestroy(idx->stats_ev);
+    if (idx->dev_h) cudaFreeHost(idx->dev_h);
     delete idx;
 }
 
@@ -1058,9 +1068,12 @@ int rmu_index_add(rmu_index* idx, const float* vecs, int64_t n, int src_is_host,
     const int wpb = 8;
     const long long blocks = (n + wpb - 1) / wpb;
     row_stats_kernel<<<static_cast<unsigned>(blocks), wpb * 32, 0, st>>>(idx->x, idx->n, n, idx->dim, idx->metric,
-                                                                          idx->rscale, idx->rbias, idx->max_norm_bits);
+                                                                          idx->rscale, idx->rbias, idx->max_norm_bits,
+                                                                          idx->max_norm_bits + 1);
     count_launch();
     RMU_CHECK_LAUNCH();
+    RMU_CUDA(cudaMemcpyAsync(idx->dev_h, idx->max_norm_bits + 1, sizeof(float), cudaMemcpyDeviceToHost, st));
+    RMU_CUDA(cudaEventRecord(idx->stats_ev, st));
     idx->n += n;
     idx->tmap_rows = -1;
     return RMU_OK;
@@ -1077,7 +1090,8 @@ int rmu_index_clear(rmu_index* idx) {
     RMU_CUDA(cudaDeviceSynchronize());
     idx->n = 0;
     idx->tmap_rows = -1;
-    RMU_CUDA(cudaMemset(idx->max_norm_bits, 0, sizeof(unsigned)));
+    RMU_CUDA(cudaMemset(idx->max_norm_bits, 0, 2 * sizeof(unsigned)));
+    *idx->dev_h = 0.f;
     return RMU_OK;
 }
 
@@ -1139,6 +1153,13 @@ int rmu_index_search(rmu_index* idx, const float* queries, int nq, int k, int64_
         return RMU_OK;
     }
 
+    // unit-norm corpora (sentence-transformers' Normalize output): cosine and L2 rank exactly like the inner
+    // product, so the scan skips the per-row scale / bias and the certificate absorbs the 1e-6 slack
+    bool unit_rows = false;
+    if (tensor_ok && idx->metric != RMU_METRIC_IP) {
+        RMU_CUDA(cudaEventSynchronize(idx->stats_ev));
+        unit_rows = *idx->dev_h < 1e-6f;
+    }
     if (tensor_ok) {
         if (idx->tmap_rows != N || idx->tmap_bn != scan_bn()) {
             if (scan_3d()) {
@@ -1156,8 +1177,8 @@ int rmu_index_search(rmu_index* idx, const float* queries, int nq, int k, int64_
         for (int q0 = 0; q0 < nq; q0 += kScanQ) {
             ScanParams sp{};
             sp.q = queries; sp.q0 = q0; sp.nq = std::min(kScanQ, nq - q0); sp.dim = D; sp.n = N; sp.ntiles = ntiles;
-            sp.rscale = idx->metric == RMU_METRIC_COSINE ? idx->rscale : nullptr;
-            sp.rbias = idx->metric == RMU_METRIC_L2 ? idx->rbias : nullptr;
+            sp.rscale = (idx->metric == RMU_METRIC_COSINE && !unit_rows) ? idx->rscale : nullptr;
+            sp.rbias = (idx->metric == RMU_METRIC_L2 && !unit_rows) ? idx->rbias : nullptr;
             sp.lists = d_scan;
             { static const char* ab = getenv("RMU_SCAN_ABLATE"); sp.ablate = ab ? atoi(ab) : 0; }
             const int grid = std::min(grid_scan, ntiles);
@@ -1192,6 +1213,7 @@ int rmu_index_search(rmu_index* idx, const float* queries, int nq, int k, int64_
             FinalizeParams fp{};
             fp.lists = d_scan; fp.nlists = grid; fp.qstride = kScanQ; fp.lstride = 2 * keep; fp.len = keep; fp.ksel = keep;
             fp.x = idx->x; fp.n = N; fp.dim = D; fp.metric = idx->metric; fp.q = queries; fp.q0 = q0; fp.exact = 0;
+            fp.unit_rows = unit_rows ? 1 : 0;
             fp.k = k; fp.id_offset = id_offset; fp.max_norm_bits = idx->max_norm_bits;
             fp.eps_rel = 2.2e-3f;   // > 2^-9: both TF32 operands truncated to 10 mantissa bits
             fp.out_scores = out_scores; fp.out_ids = reinterpret_cast<long long*>(out_ids); fp.flags = d_flags;

@@ -20,7 +20,7 @@ import numpy as np
 
 from . import _lib
 from .encoder import MAX_TOKENS_PER_CALL, BertEncoder
-from .tokenizer import encode_ragged, load_tokenizer
+from .tokenizer import RaggedTokenizer, load_tokenizer
 from .weights import resolve_model
 
 
@@ -55,6 +55,7 @@ class HuggingFaceEmbeddings:
         self.normalize = bool(normalize or self.encode_kwargs.get("normalize_embeddings", False))
         self.max_seq_length = int(max_len)
         self.tokenizer = load_tokenizer(vocab_src, cfg.vocab_size)
+        self._ragged = RaggedTokenizer(self.tokenizer, self.max_seq_length)
         self.client = BertEncoder(cfg, w, with_head=False, device=device)
 
     # -- tensor fast path (additional to the reference surface)
@@ -64,7 +65,7 @@ class HuggingFaceEmbeddings:
         if len(texts) == 0:
             return torch.empty((0, self.config.hidden), dtype=torch.float32, device=self.client.device)
         texts = [t.replace("\n", " ").strip() for t in texts]
-        ids, typ, cu = encode_ragged(self.tokenizer, texts, None, self.max_seq_length)
+        ids, typ, cu = self._ragged(texts)
         outs = []
         for s, e in BertEncoder._chunks(cu, MAX_TOKENS_PER_CALL):
             t0, t1 = int(cu[s]), int(cu[e])
@@ -77,7 +78,7 @@ class HuggingFaceEmbeddings:
         if len(texts) == 0:
             return np.zeros((0, self.config.hidden), dtype=np.float32)
         texts = [t.replace("\n", " ").strip() for t in texts]
-        ids, typ, cu = encode_ragged(self.tokenizer, texts, None, self.max_seq_length)
+        ids, typ, cu = self._ragged(texts)
         return self.client.embed_host(ids, typ, cu, self.pooling, self.normalize)
 
     # -- the reference surface

@@ -94,9 +94,26 @@ def synthetic_sentences(vocab: Dict[str, int], n: int, min_words: int, max_words
     return out
 
 
+class RaggedTokenizer:
+    """A PRIVATE copy of a tokenizer, configured once (truncation='longest_first' to max_length, no
+    padding) and never mutated afterwards, so any number of request threads can tokenise through it
+    (Flask serves /chat on several threads over one shared RAGHelper: server/server.py:141-146,394;
+    mutating a shared `tokenizers.Tokenizer` while another thread encodes raises "Already borrowed")."""
+
+    def __init__(self, tok: Tokenizer, max_length: int):
+        self.max_length = int(max_length)
+        self._tok = Tokenizer.from_str(tok.to_str())
+        self._tok.enable_truncation(max_length=self.max_length, strategy="longest_first")
+        self._tok.no_padding()
+
+    def __call__(self, texts_a: Sequence[str], texts_b: Optional[Sequence[str]] = None):
+        return _pack(self._tok.encode_batch(list(texts_a) if texts_b is None else list(zip(texts_a, texts_b))))
+
+
 def encode_ragged(tok: Tokenizer, texts_a: Sequence[str], texts_b: Optional[Sequence[str]],
                   max_length: int) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
-    """Tokenise with truncation='longest_first', NO padding, and pack.
+    """Tokenise with truncation='longest_first', NO padding, and pack (single-threaded helper: it
+    re-configures `tok`; the drop-in classes use RaggedTokenizer instead).
 
     Returns (ids int32 [T], type_ids int32 [T], cu_seqlens int32 [B+1])."""
     tok.enable_truncation(max_length=max_length, strategy="longest_first")
@@ -105,6 +122,10 @@ def encode_ragged(tok: Tokenizer, texts_a: Sequence[str], texts_b: Optional[Sequ
         enc = tok.encode_batch(list(texts_a))
     else:
         enc = tok.encode_batch(list(zip(texts_a, texts_b)))
+    return _pack(enc)
+
+
+def _pack(enc) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
     lens = np.fromiter((len(e.ids) for e in enc), dtype=np.int64, count=len(enc))
     cu = np.zeros(len(enc) + 1, dtype=np.int32)
     np.cumsum(lens, out=cu[1:])
