@@ -63,7 +63,7 @@ static int launch_bn(const SplitOperand& A, const SplitOperand& W, const GemmPar
     ProfScope _ps(PROF_GEMM, st);
     const CUtensorMap& wh = BN == 128 ? W.map_hi : BN == 192 ? W.map192_hi : W.map256_hi;
     const CUtensorMap& wl = BN == 128 ? W.map_lo : BN == 192 ? W.map192_lo : W.map256_lo;
-    kern<<<grid, kGemmThreads, kGemmSmem, st>>>(A.map_hi, A.map_lo, wh, wl, p);
+    kern<<<grid, 64 + 32 * gemm_epi_warps<MODE, BN>(), kGemmSmem, st>>>(A.map_hi, A.map_lo, wh, wl, p);
     count_launch();
     RMU_CHECK_LAUNCH();
     return RMU_OK;

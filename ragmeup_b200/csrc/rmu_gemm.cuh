@@ -63,8 +63,13 @@ __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + e
 
 // BN = output-tile width (MMA N): 128 (3 stages of 64 KB), 192 (2 x 80 KB) or 256 (2 x 96 KB).  Wider tiles read
 // the A slab once for more columns: L2->SM bytes per MMA cycle 85 -> 69 -> 62, smem operand reads 128 -> 104 -> 94.
+// The erf-GELU epilogue (FFN-in) is ALU / issue bound: with 192-wide tiles it runs 12 epilogue warps (three per
+// TMEM lane quadrant, two column chunks each) instead of 8.
 template <int MODE, int BN>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+__host__ __device__ constexpr int gemm_epi_warps() { return (MODE == GEMM_BIAS_GELU_SPLIT && BN == 192) ? 12 : kGemmEpiWarps; }
+
+template <int MODE, int BN>
+__global__ void __launch_bounds__(64 + 32 * gemm_epi_warps<MODE, BN>(), 1)
 gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tAh, const __grid_constant__ CUtensorMap tAl,
                   const __grid_constant__ CUtensorMap tWh, const __grid_constant__ CUtensorMap tWl,
                   const GemmParams p) {
@@ -74,10 +79,14 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tAh, const __grid_constant
     constexpr int kWPlane = BN * 128;                              // one W plane of a stage
     constexpr int kGemmStageBytes = 2 * kGemmPlaneBytes + 2 * kWPlane;
     constexpr int kTmemCols = BN == 128 ? 256 : 512;
+    constexpr int kEpi = gemm_epi_warps<MODE, BN>();
+    constexpr int kChunksPerWarp = (BN / 32) / (kEpi / 4);
+    constexpr size_t kStagingBytes = static_cast<size_t>(kEpi) * 32 * kGemmStageRow * sizeof(float);
+    static_assert(static_cast<size_t>(kGemmStages) * kGemmStageBytes + kStagingBytes + 256 + 1024 <= kGemmSmem, "smem budget");
     extern __shared__ uint8_t gemm_smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(gemm_smem_raw) + 1023) & ~uintptr_t(1023));
     float* staging = reinterpret_cast<float*>(smem + kGemmStages * kGemmStageBytes);
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + kGemmStages * kGemmStageBytes + kGemmStagingBytes);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + kGemmStages * kGemmStageBytes + kStagingBytes);
     uint64_t* empty = full + kGemmStages;
     uint64_t* acc_full = empty + kGemmStages;
     uint64_t* acc_empty = acc_full + 2;
@@ -87,7 +96,7 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tAh, const __grid_constant
     const unsigned lane = lane_id();
     if (threadIdx.x == 0) {
         for (int i = 0; i < kGemmStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 32 * kGemmEpiWarps); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 32 * kEpi); }
         fence_mbar_init();
         prefetch_tmap(&tAh); prefetch_tmap(&tAl); prefetch_tmap(&tWh); prefetch_tmap(&tWl);
     }
@@ -170,8 +179,8 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tAh, const __grid_constant
             tc_fence_after();
             const int row_base = mb * kGemmBM + quad * 32;
 #pragma unroll 1
-            for (int cc = 0; cc < BN / 64; ++cc) {
-                const int c = chalf * (BN / 64) + cc;
+            for (int cc = 0; cc < kChunksPerWarp; ++cc) {
+                const int c = chalf * kChunksPerWarp + cc;
                 const int col0 = nb * kGemmBN + c * 32;
                 // residual rows of this chunk: issued first so their latency hides behind the TMEM read
                 __half2 rsh[16], rsl[16];
@@ -190,7 +199,7 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tAh, const __grid_constant
                 uint32_t r[32];
                 tmem_ld32(tmem_addr(tmem_base, quad * 32, buf * kGemmBN + c * 32), r);
                 tmem_ld_wait();
-                if (cc == BN / 64 - 1) {             // last TMEM read of this warp for the tile
+                if (cc == kChunksPerWarp - 1) {      // last TMEM read of this warp for the tile
                     tc_fence_before();
                     mbar_arrive(&acc_empty[buf]);
                 }

@@ -251,6 +251,12 @@ struct ScanParams {
     // subset of the rows, hence a valid lower bound of the final KEEP-th best key).
     int phase, lead;
     const float* tau0;     // [nq_total]
+    // K split for 384 < dim <= 768 (the query block only has 384 TMEM columns): pass 1 multiplies columns
+    // [0, 384) and stores raw partial scores, pass 2 multiplies [384, dim) and adds them before thresholding.
+    int kcol0, kdim;       // first column and number of columns of this launch
+    int kpass;             // 0 single pass, 1 write partials only, 2 add partials then continue as usual
+    float* partial;        // [128][npad] raw partial scores of the current query block
+    long long npad;        // row pitch of `partial` (multiple of 32)
 };
 
 // BN rows per tile (= MMA N), NBUF TMEM accumulators, NSLAB pipeline stages, each stage = KD K-blocks
@@ -275,7 +281,7 @@ scan_tf32_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
 
     const int warp = threadIdx.x >> 5;
     const unsigned lane = lane_id();
-    const int KB = (p.dim + 31) / 32;   // 128-byte K blocks per row
+    const int KB = (p.kdim + 31) / 32;  // 128-byte K blocks of this launch's column range
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < NSLAB; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
@@ -304,7 +310,7 @@ scan_tf32_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 const int d = c * 8 + j;
-                r[j] = (qrow != nullptr && d < p.dim) ? __float_as_uint(qrow[d]) : 0u;
+                r[j] = (qrow != nullptr && d < p.kdim) ? __float_as_uint(qrow[p.kcol0 + d]) : 0u;
             }
             tmem_st8(tmem_addr(tmem_base, quad * 32, c * 8), r);
         }
@@ -330,7 +336,7 @@ scan_tf32_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
                         // out of bounds and arrive as zeros, still counting their bytes)
 #pragma unroll
                         for (int kk = 0; kk < KD; ++kk)
-                            tma_load_2d(slabs + slot * SLAB_BYTES + kk * (BN * 128), &tmap, (kb + kk) * 32, t * BN,
+                            tma_load_2d(slabs + slot * SLAB_BYTES + kk * (BN * 128), &tmap, p.kcol0 + (kb + kk) * 32, t * BN,
                                         &full[slot], kEvictFirst);
                     }
                     if (++slot == NSLAB) { slot = 0; phase ^= 1; }
@@ -358,7 +364,7 @@ scan_tf32_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
                         const uint64_t bdesc = umma_desc_sw128_kmajor(smem_u32(slabs + slot * SLAB_BYTES + kk * (BN * 128)));
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
-                            if (kb * 32 + k * 8 < p.dim && !(p.ablate & 1)) {
+                            if (kb * 32 + k * 8 < p.kdim && !(p.ablate & 1)) {
                                 mma_tf32_ts(d_addr, tmem_base + kb * 32 + k * 8, bdesc + static_cast<uint64_t>(k * 2),
                                             IDESC, (kb | k) != 0 ? 1u : 0u);
                             }
@@ -398,6 +404,27 @@ scan_tf32_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
                 }
                 if (p.ablate & 2) continue;
                 const long long row0 = static_cast<long long>(t) * BN + c * 32;
+                if (p.kpass == 1) {                       // first K half: park the raw partial scores
+                    if (live && row0 < p.n) {
+                        float4* dst = reinterpret_cast<float4*>(p.partial + static_cast<long long>(qi) * p.npad + row0);
+#pragma unroll
+                        for (int g4 = 0; g4 < 8; ++g4)
+                            dst[g4] = make_float4(__uint_as_float(r[4 * g4]), __uint_as_float(r[4 * g4 + 1]),
+                                                  __uint_as_float(r[4 * g4 + 2]), __uint_as_float(r[4 * g4 + 3]));
+                    }
+                    continue;
+                }
+                if (p.kpass == 2 && live && row0 < p.n) { // second K half: add what the first half parked
+                    const float4* src = reinterpret_cast<const float4*>(p.partial + static_cast<long long>(qi) * p.npad + row0);
+#pragma unroll
+                    for (int g4 = 0; g4 < 8; ++g4) {
+                        const float4 v = src[g4];
+                        r[4 * g4] = __float_as_uint(__uint_as_float(r[4 * g4]) + v.x);
+                        r[4 * g4 + 1] = __float_as_uint(__uint_as_float(r[4 * g4 + 1]) + v.y);
+                        r[4 * g4 + 2] = __float_as_uint(__uint_as_float(r[4 * g4 + 2]) + v.z);
+                        r[4 * g4 + 3] = __float_as_uint(__uint_as_float(r[4 * g4 + 3]) + v.w);
+                    }
+                }
                 if (p.dbg != nullptr && blockIdx.x == 0 && t == t0) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j) p.dbg[qi * BN + c * 32 + j] = __uint_as_float(r[j]);
@@ -442,8 +469,10 @@ scan_tf32_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
             }
         }
         // final: every list sorted descending, zero padded to KEEP entries
-        warp_compact<KEEP, CAP>(mybuf, cnt, tau, true);
-        for (int e = cnt; e < KEEP; ++e) mybuf[e] = 0ull;
+        if (p.kpass != 1) {
+            warp_compact<KEEP, CAP>(mybuf, cnt, tau, true);
+            for (int e = cnt; e < KEEP; ++e) mybuf[e] = 0ull;
+        }
     }
 
     tc_fence_before();
@@ -1111,7 +1140,9 @@ int rmu_index_search(rmu_index* idx, const float* queries, int nq, int k, int64_
     const int D = idx->dim;
     const long long N = idx->n;
     // tensor scan eligibility: TMA row pitch multiple of 16 B, query block fits TMEM, enough rows, k small
-    const bool tensor_ok = (D % 4 == 0) && D <= kScanACols && N >= 16384 && k <= 128 && mode != RMU_SEARCH_EXACT;
+    const bool tensor_ok = (D % 4 == 0) && D <= 2 * kScanACols && N >= 16384 && k <= 128 && mode != RMU_SEARCH_EXACT &&
+                           (D <= kScanACols || !scan_3d());   // the K-split passes use the 2-D tensor map
+    const bool ksplit = tensor_ok && D > kScanACols;
     const int keep = keep_for_k(k);                       // tensor: candidates kept per query (>= 3k)
     int keepx = 32; while (keepx < k) keepx <<= 1;        // exact: per-chunk list length (>= k)
     const int nchunks = static_cast<int>((N + kChunk - 1) / kChunk);
@@ -1125,6 +1156,8 @@ int rmu_index_search(rmu_index* idx, const float* queries, int nq, int k, int64_
     const size_t o_nsel = carve(sizeof(int) * 4);
     const size_t o_scan = tensor_ok ? carve(sizeof(unsigned long long) * grid_scan * kScanQ * 2 * keep) : 0;
     const size_t o_tau = carve(sizeof(float) * nq);
+    const long long npad = (N + 31) / 32 * 32;
+    const size_t o_part = ksplit ? carve(sizeof(float) * kScanQ * static_cast<size_t>(npad)) : 0;
     const size_t o_exact = carve(sizeof(unsigned long long) * std::max(nchunks, 1) * static_cast<size_t>(nq) * keepx);
     int rc = ensure_ws(idx, off);
     if (rc != RMU_OK) return rc;
@@ -1135,6 +1168,7 @@ int rmu_index_search(rmu_index* idx, const float* queries, int nq, int k, int64_
     unsigned long long* d_scan = reinterpret_cast<unsigned long long*>(ws + o_scan);
     unsigned long long* d_exact = reinterpret_cast<unsigned long long*>(ws + o_exact);
     float* d_tau0 = reinterpret_cast<float*>(ws + o_tau);
+    float* d_part = reinterpret_cast<float*>(ws + o_part);
 
     const size_t qsmem = static_cast<size_t>(D) * sizeof(float);
     int scan_launches = 0;
@@ -1174,6 +1208,21 @@ int rmu_index_search(rmu_index* idx, const float* queries, int nq, int k, int64_
             idx->tmap_bn = scan_bn();
         }
         const int ntiles = static_cast<int>((N + scan_bn() - 1) / scan_bn());
+        // one logical scan = one launch, or two when dim > 384 (K split: park partial scores, then finish)
+        auto scan_launch = [&](int keep_x, ScanParams sp, int grid) -> int {
+            sp.partial = d_part; sp.npad = npad;
+            if (!ksplit) {
+                sp.kcol0 = 0; sp.kdim = D; sp.kpass = 0;
+                ++scan_launches;
+                return dispatch_scan(keep_x, idx->tmap, sp, grid, st);
+            }
+            sp.kcol0 = 0; sp.kdim = kScanACols; sp.kpass = 1;
+            int r = dispatch_scan(keep_x, idx->tmap, sp, grid, st);
+            if (r != RMU_OK) return r;
+            sp.kcol0 = kScanACols; sp.kdim = D - kScanACols; sp.kpass = 2;
+            scan_launches += 2;
+            return dispatch_scan(keep_x, idx->tmap, sp, grid, st);
+        };
         for (int q0 = 0; q0 < nq; q0 += kScanQ) {
             ScanParams sp{};
             sp.q = queries; sp.q0 = q0; sp.nq = std::min(kScanQ, nq - q0); sp.dim = D; sp.n = N; sp.ntiles = ntiles;
@@ -1194,21 +1243,19 @@ int rmu_index_search(rmu_index* idx, const float* queries, int nq, int k, int64_
             if (exchange) {
                 sp.phase = 1;
                 sp.lead = std::max(2, (tiles_per_cta * lead_pct + 99) / 100);
-                rc = dispatch_scan(kLeadKeep, idx->tmap, sp, grid, st);
+                rc = scan_launch(kLeadKeep, sp, grid);
                 if (rc != RMU_OK) return rc;
                 { ProfScope _ps(PROF_FINALIZE, st);
                 select_tau_kernel<<<sp.nq, 256, 0, st>>>(d_scan, grid, scan_cap(kLeadKeep), kLeadKeep, keep, q0, d_tau0); }
                 count_launch();
                 RMU_CHECK_LAUNCH();
                 sp.phase = 2;
-                rc = dispatch_scan(keep, idx->tmap, sp, grid, st);
+                rc = scan_launch(keep, sp, grid);
                 if (rc != RMU_OK) return rc;
-                scan_launches += 2;
             } else {
                 sp.phase = 0;
-                rc = dispatch_scan(keep, idx->tmap, sp, grid, st);
+                rc = scan_launch(keep, sp, grid);
                 if (rc != RMU_OK) return rc;
-                ++scan_launches;
             }
             FinalizeParams fp{};
             fp.lists = d_scan; fp.nlists = grid; fp.qstride = kScanQ; fp.lstride = 2 * keep; fp.len = keep; fp.ksel = keep;
@@ -1290,7 +1337,7 @@ int rmu_debug_scan_tile(rmu_index* idx, const float* queries, int nq, float* out
     idx->tmap_bn = scan_bn();
     ScanParams sp{};
     sp.q = queries; sp.q0 = 0; sp.nq = nq; sp.dim = idx->dim; sp.n = idx->n; sp.ntiles = 1;
-    sp.lists = static_cast<unsigned long long*>(idx->ws); sp.dbg = out;
+    sp.lists = static_cast<unsigned long long*>(idx->ws); sp.dbg = out; sp.kcol0 = 0; sp.kdim = idx->dim; sp.kpass = 0;
     return dispatch_scan(64, idx->tmap, sp, 1, st);
 }
 

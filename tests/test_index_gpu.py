@@ -86,6 +86,27 @@ def test_tensor_scan_equals_exact_and_oracle(cuda, metric, n, nq, k):
         _check(s1, i1, rs, ri)
 
 
+@pytest.mark.parametrize("metric", ["ip", "cosine", "l2"])
+@pytest.mark.parametrize("dim,n,nq,k", [(768, 20_000, 5, 10), (400, 17_000, 130, 20), (768, 33_000, 64, 50)])
+def test_k_split_scan_for_wide_vectors(cuda, metric, dim, n, nq, k):
+    """384 < dim <= 768 (bge-base 768-d, config 5): the tensor scan runs two K passes (partial scores parked
+    in HBM); results must still be bit-identical to the exact fp32 scan"""
+    from ragmeup_b200.index import MODE_AUTO, MODE_EXACT
+    g = torch.Generator(device="cuda").manual_seed(dim + n)
+    x = torch.nn.functional.normalize(torch.randn(n, dim, device="cuda", generator=g), dim=1)
+    if metric == "l2":
+        x = x * (1.0 + 0.2 * torch.rand(n, 1, device="cuda", generator=g))     # non-unit rows: per-row bias path
+    x[n - 3] = x[5]
+    q = torch.nn.functional.normalize(torch.randn(nq, dim, device="cuda", generator=g), dim=1)
+    q[0] = x[5]
+    ix = _idx(cuda, x, metric)
+    s0, i0 = ix.search(q, k, mode=MODE_EXACT)
+    s1, i1 = ix.search(q, k, mode=MODE_AUTO, want_stats=True)
+    assert ix.last_stats[1] >= 2                      # two launches per logical scan
+    assert (i0 == i1).all() and (s0 == s1).all()
+    _check_topk_fp64(s1, i1, q.cpu().numpy(), x.cpu().numpy(), k, metric)
+
+
 def test_certificate_falls_back_on_near_duplicates(cuda):
     """more near-ties than the coarse pass keeps: the certificate must fail and the exact fp32 scan must
     answer (bit-identical to MODE_EXACT; valid top-k in float64 up to fp32 near-ties)"""

@@ -3,16 +3,16 @@ import os, sys, time
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from ragmeup_b200.index import FlatIndex, MODE_AUTO
-N = int(os.environ.get("PROF_N", 10_000_000)); Q = int(os.environ.get("PROF_Q", 128)); K = int(os.environ.get("PROF_K", 10))
+N = int(os.environ.get("PROF_N", 10_000_000)); Q = int(os.environ.get("PROF_Q", 128)); K = int(os.environ.get("PROF_K", 10)); D = int(os.environ.get("PROF_D", 384))
 IT = int(os.environ.get("PROF_ITERS", 3)); metric = os.environ.get("PROF_METRIC", "ip")
 dev = torch.device("cuda")
 def unit(n, d, seed):
     g = torch.Generator(device=dev).manual_seed(seed)
     return torch.nn.functional.normalize(torch.randn(n, d, generator=g, device=dev), dim=1)
-ix = FlatIndex(384, metric); ix.reserve(N)
+ix = FlatIndex(D, metric); ix.reserve(N)
 for b in range(0, N, 1_000_000):
-    ix.add(unit(min(1_000_000, N - b), 384, 100 + b // 1_000_000))
-qs = unit(Q, 384, 5)
+    ix.add(unit(min(1_000_000, N - b), D, 100 + b // 1_000_000))
+qs = unit(Q, D, 5)
 torch.cuda.synchronize()
 ts = []
 for it in range(IT):
@@ -20,4 +20,4 @@ for it in range(IT):
     e0.record(); ix.search(qs, K, mode=MODE_AUTO); e1.record(); torch.cuda.synchronize()
     ts.append(e0.elapsed_time(e1))
 print(f"variant={os.environ.get('RMU_SCAN_VARIANT','0')} N={N} Q={Q} k={K} {metric}: ms per search {['%.3f' % t for t in ts]}  "
-      f"{4.0*N*384/(min(ts)*1e-3)/1e9:.0f} GB/s", flush=True)
+      f"{4.0*N*D/(min(ts)*1e-3)/1e9:.0f} GB/s D={D}", flush=True)
