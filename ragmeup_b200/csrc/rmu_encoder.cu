@@ -34,9 +34,10 @@ __global__ void split_planes_kernel(const float* __restrict__ src, __half* __res
 
 constexpr int kMaxPerLane = 32;  // hidden <= 1024
 
-// LayerNorm of one row.  Lane l holds the CONTIGUOUS elements x[l*per_lane .. +per_lane) (per_lane % 4 == 0),
-// so loads are float4 and the split planes are written 8 bytes at a time.  Biased variance, eps inside
-// the sqrt (nn.LayerNorm).
+// LayerNorm of one row (H % 128 == 0).  Lane l holds float4 chunks l, l + 32, l + 64 ... of the row
+// (element v[i] is column ((i / 4) * 32 + l) * 4 + i % 4), so every warp load is one contiguous 512-byte
+// segment and every plane store one contiguous 256-byte segment.  Biased variance, eps inside the sqrt
+// (nn.LayerNorm).
 __device__ __forceinline__ void warp_layernorm_store(float (&v)[kMaxPerLane], int per_lane, int H, float eps,
                                                      const float* __restrict__ g, const float* __restrict__ b,
                                                      __half* __restrict__ hi, __half* __restrict__ lo) {
@@ -51,12 +52,12 @@ __device__ __forceinline__ void warp_layernorm_store(float (&v)[kMaxPerLane], in
     for (int i = 0; i < kMaxPerLane; ++i) if (i < per_lane) { const float d = v[i] - mean; q = fmaf(d, d, q); }
     for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
     const float rstd = 1.0f / sqrtf(q / static_cast<float>(H) + eps);
-    const int d0 = lane * per_lane;
 #pragma unroll
     for (int i = 0; i < kMaxPerLane; i += 4) {
         if (i < per_lane) {
-            const float4 gg = *reinterpret_cast<const float4*>(g + d0 + i);
-            const float4 bb = *reinterpret_cast<const float4*>(b + d0 + i);
+            const int col = (i * 8 + static_cast<int>(lane)) * 4;      // (i / 4) * 32 + lane, in float4 units
+            const float4 gg = *reinterpret_cast<const float4*>(g + col);
+            const float4 bb = *reinterpret_cast<const float4*>(b + col);
             const float y0 = (v[i] - mean) * rstd * gg.x + bb.x, y1 = (v[i + 1] - mean) * rstd * gg.y + bb.y;
             const float y2 = (v[i + 2] - mean) * rstd * gg.z + bb.z, y3 = (v[i + 3] - mean) * rstd * gg.w + bb.w;
             __half h0, l0, h1, l1, h2, l2, h3, l3;
@@ -66,8 +67,8 @@ __device__ __forceinline__ void warp_layernorm_store(float (&v)[kMaxPerLane], in
             uint2 ph, pl;
             ph.x = *reinterpret_cast<uint32_t*>(&ha); ph.y = *reinterpret_cast<uint32_t*>(&hb);
             pl.x = *reinterpret_cast<uint32_t*>(&la); pl.y = *reinterpret_cast<uint32_t*>(&lb);
-            *reinterpret_cast<uint2*>(hi + d0 + i) = ph;
-            *reinterpret_cast<uint2*>(lo + d0 + i) = pl;
+            *reinterpret_cast<uint2*>(hi + col) = ph;
+            *reinterpret_cast<uint2*>(lo + col) = pl;
         }
     }
 }
@@ -93,17 +94,17 @@ __global__ void embed_ln_kernel(const int* __restrict__ ids, const int* __restri
     int ty = type_ids ? type_ids[t] : 0;
     ty = ty < 0 ? 0 : (ty >= type_vocab ? type_vocab - 1 : ty);
     const int per_lane = H >> 5;
-    const int d0 = lane_id() * per_lane;
-    const float* w = word + static_cast<size_t>(id) * H + d0;
-    const float* pp = pos + static_cast<size_t>(p) * H + d0;
-    const float* tt = typ + static_cast<size_t>(ty) * H + d0;
+    const int l4 = static_cast<int>(lane_id()) * 4;
+    const float* w = word + static_cast<size_t>(id) * H + l4;
+    const float* pp = pos + static_cast<size_t>(p) * H + l4;
+    const float* tt = typ + static_cast<size_t>(ty) * H + l4;
     float v[kMaxPerLane];
 #pragma unroll
     for (int i = 0; i < kMaxPerLane; i += 4) {
         if (i < per_lane) {
-            const float4 a = *reinterpret_cast<const float4*>(w + i);
-            const float4 c = *reinterpret_cast<const float4*>(tt + i);
-            const float4 e = *reinterpret_cast<const float4*>(pp + i);
+            const float4 a = *reinterpret_cast<const float4*>(w + i * 32);
+            const float4 c = *reinterpret_cast<const float4*>(tt + i * 32);
+            const float4 e = *reinterpret_cast<const float4*>(pp + i * 32);
             // HF: inputs_embeds + token_type_embeddings, then + position_embeddings
             v[i] = (a.x + c.x) + e.x; v[i + 1] = (a.y + c.y) + e.y; v[i + 2] = (a.z + c.z) + e.z; v[i + 3] = (a.w + c.w) + e.w;
         }
@@ -117,12 +118,12 @@ __global__ void ln_kernel(const float* __restrict__ pre, int T, int H, const flo
     const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (t >= T) return;
     const int per_lane = H >> 5;
-    const float* row = pre + static_cast<size_t>(t) * H + lane_id() * per_lane;
+    const float* row = pre + static_cast<size_t>(t) * H + lane_id() * 4;
     float v[kMaxPerLane];
 #pragma unroll
     for (int i = 0; i < kMaxPerLane; i += 4) {
         if (i < per_lane) {
-            const float4 a = *reinterpret_cast<const float4*>(row + i);
+            const float4 a = *reinterpret_cast<const float4*>(row + i * 32);
             v[i] = a.x; v[i + 1] = a.y; v[i + 2] = a.z; v[i + 3] = a.w;
         }
     }
@@ -448,8 +449,12 @@ __device__ __forceinline__ float fast_exp2(float x) {   // ex2.approx: 2 ulp, ex
     return y;
 }
 
-template <int DH>
-__global__ void __launch_bounds__(kAttWarps * 32) attention_planes_kernel(const __half* __restrict__ ph, const __half* __restrict__ pl,
+// MINB = CTAs per SM the register allocation is bounded for (d_h = 32: 2 -> 95 registers, no spills; bounding it
+// to 3 CTAs / 64 registers spills in the key loop and measured 541 us instead of 352 us per layer call).
+// Grid = (heads, sequences, row blocks): the heads of one sequence run together, so the 64-byte (d_h = 32)
+// K / V row segments of neighbouring heads are fetched from DRAM as whole lines.
+template <int DH, int MINB>
+__global__ void __launch_bounds__(kAttWarps * 32, MINB) attention_planes_kernel(const __half* __restrict__ ph, const __half* __restrict__ pl,
                                                                           const int* __restrict__ cu, int H, int ksb,
                                                                           __half* __restrict__ ctx_hi, __half* __restrict__ ctx_lo) {
     constexpr int KSTR = DH + 8;
@@ -461,7 +466,7 @@ __global__ void __launch_bounds__(kAttWarps * 32) attention_planes_kernel(const 
     __half* Vh = Kl + ksb * KSTR;
     __half* Vl = Vh + ksb * KSTR;
 
-    const int b = blockIdx.x, h = blockIdx.y;
+    const int b = blockIdx.y, h = blockIdx.x;
     const int t0 = cu[b], S = cu[b + 1] - t0;
     const int rbase = blockIdx.z * (kAttWarps * 16);
     if (rbase >= S) return;
@@ -855,21 +860,20 @@ static int run_encoder(rmu_encoder* e, const int32_t* ids, const int32_t* type_i
         {
             ProfScope _ps(PROF_ATTN, st);
             if (attn_mode == 0) {
-                dim3 pg(static_cast<unsigned>(B), static_cast<unsigned>(c.heads),
+                dim3 pg(static_cast<unsigned>(c.heads), static_cast<unsigned>(B),
                         static_cast<unsigned>((max_seqlen + kAttWarps * 16 - 1) / (kAttWarps * 16)));
                 // keys resident per CTA: the whole (longest) sequence when it fits, else super-blocks of kKeySB
                 const int ksb = std::min(kKeySB, (max_seqlen + 31) / 32 * 32);
                 const size_t smem_max = 4 * sizeof(__half) * static_cast<size_t>(kKeySB) * (DH + 8);
                 const size_t smem = 4 * sizeof(__half) * static_cast<size_t>(ksb) * (DH + 8);
-                if (DH == 32) {
-                    static bool set32 = false;
-                    if (!set32) { RMU_CUDA(cudaFuncSetAttribute(attention_planes_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_max))); set32 = true; }
-                    attention_planes_kernel<32><<<pg, kAttWarps * 32, smem, st>>>(e->QKVP.hi, e->QKVP.lo, cu, H, ksb, e->CTX.hi, e->CTX.lo);
-                } else {
-                    static bool set64 = false;
-                    if (!set64) { RMU_CUDA(cudaFuncSetAttribute(attention_planes_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_max))); set64 = true; }
-                    attention_planes_kernel<64><<<pg, kAttWarps * 32, smem, st>>>(e->QKVP.hi, e->QKVP.lo, cu, H, ksb, e->CTX.hi, e->CTX.lo);
+                auto kern = DH == 32 ? attention_planes_kernel<32, 2> : attention_planes_kernel<64, 1>;   // d_h = 64 needs > 96 registers
+                static bool attr_set[2] = {false, false};
+                const int ki = DH == 32 ? 0 : 1;
+                if (!attr_set[ki]) {
+                    RMU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_max)));
+                    attr_set[ki] = true;
                 }
+                kern<<<pg, kAttWarps * 32, smem, st>>>(e->QKVP.hi, e->QKVP.lo, cu, H, ksb, e->CTX.hi, e->CTX.lo);
             } else if (attn_mode == 2) {
                 if (DH == 32) attention_kernel<32><<<ag, 128, 0, st>>>(e->QKV, cu, H, scale, e->CTX.hi, e->CTX.lo);
                 else attention_kernel<64><<<ag, 128, 0, st>>>(e->QKV, cu, H, scale, e->CTX.hi, e->CTX.lo);
