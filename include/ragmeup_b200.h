@@ -100,6 +100,30 @@ int rmu_topk_merge(const float* scores, const int64_t* ids, int R, int nq, int k
 int rmu_mmr_select(const float* q, const float* cand, const int32_t* n_cand, int nq, int fetch_k, int dim,
                    int k, float lambda_mult, int32_t* out_sel, void* stream);
 
+/* ------------------------------------------------------------------ BM25 sparse leg
+ * Stands behind langchain_community.retrievers.BM25Retriever (rank_bm25.BM25Okapi.get_scores /
+ * get_top_n), built at server/RAGHelper.py:436-443 and queried through the EnsembleRetriever
+ * (:501-503).  The inverted index is CSR by term: postings of term t are
+ * post_doc/post_tf[post_ptr[t] .. post_ptr[t+1]) with documents ascending; den[d] =
+ * k1 * (1 - b + b * doc_len[d] / avgdl) and idf[t] are float64, computed by the host exactly as
+ * rank_bm25 does.  Scores are float64 and bit-identical to rank_bm25's; results are ordered score
+ * descending, equal scores by larger document index (numpy stable argsort reversed). */
+typedef struct rmu_bm25 rmu_bm25;
+int rmu_bm25_create(int64_t n_docs, int64_t n_terms, const int64_t* post_ptr_h, const int32_t* post_doc_h,
+                    const int32_t* post_tf_h, const double* den_h, const double* idf_h, double k1_plus_1,
+                    rmu_bm25** out);                    /* host arrays, copied to the device */
+int rmu_bm25_destroy(rmu_bm25* h);
+int64_t rmu_bm25_size(const rmu_bm25* h);
+int64_t rmu_bm25_terms(const rmu_bm25* h);
+/* Q queries: terms of query i are q_terms[q_ptr[i] .. q_ptr[i+1]) (term ids in query order, repeats
+ * kept); out_scores [Q, k] float64, out_ids [Q, k] int64 document numbers, -1 padded when the corpus
+ * has fewer than k documents.  1 <= k <= 256.  Device pointers: */
+int rmu_bm25_search(rmu_bm25* h, const int32_t* q_ptr, const int32_t* q_terms, int Q, int k, double* out_scores,
+                    int64_t* out_ids, void* stream);
+/* the same with HOST buffers (copies + synchronise inside the call) */
+int rmu_bm25_search_host(rmu_bm25* h, const int32_t* q_ptr_h, const int32_t* q_terms_h, int Q, int k,
+                         double* out_scores_h, int64_t* out_ids_h, void* stream);
+
 /* ------------------------------------------------------------------ BERT encoder
  * Stands behind HuggingFaceEmbeddings.embed_documents/embed_query (sentence-transformers
  * encode -> BertModel -> Pooling -> Normalize) and HuggingFaceCrossEncoder.score

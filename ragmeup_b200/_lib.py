@@ -53,6 +53,15 @@ SIGNATURES = {
                                  C.c_void_p]),
     "rmu_mmr_select": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
                                  C.c_void_p, C.c_void_p]),
+    "rmu_bm25_create": (C.c_int, [C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                  C.c_double, C.POINTER(C.c_void_p)]),
+    "rmu_bm25_destroy": (C.c_int, [C.c_void_p]),
+    "rmu_bm25_size": (C.c_int64, [C.c_void_p]),
+    "rmu_bm25_terms": (C.c_int64, [C.c_void_p]),
+    "rmu_bm25_search": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                  C.c_void_p]),
+    "rmu_bm25_search_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                       C.c_void_p]),
     "rmu_encoder_create": (C.c_int, [C.POINTER(BertConfigC), C.POINTER(C.c_void_p), C.c_int, C.c_int,
                                      C.POINTER(C.c_void_p)]),
     "rmu_encoder_destroy": (None, [C.c_void_p]),

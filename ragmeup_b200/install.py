@@ -8,6 +8,8 @@
     from langchain_postgres.vectorstores import PGVector                     RAGHelper.py:29
     from langchain_community.cross_encoders import HuggingFaceCrossEncoder   RAGHelper.py:12
     from ScoredCrossEncoderReranker import ScoredCrossEncoderReranker        RAGHelper.py:33
+    from langchain_community.retrievers import BM25Retriever                 RAGHelper.py:24
+    from langchain.retrievers import ContextualCompressionRetriever, EnsembleRetriever   RAGHelper.py:10
 
 Calling ``install()`` before ``import RAGHelper_local`` registers same-named modules in
 ``sys.modules`` so those files run unchanged with ``vector_store=milvus`` (or ``postgres``).
@@ -39,14 +41,17 @@ def _module(name: str, **attrs: Any) -> types.ModuleType:
 
 
 def build_classes() -> Dict[str, Any]:
-    """The five drop-in classes, re-based on LangChain's ABCs when LangChain is importable."""
+    """The drop-in classes, re-based on LangChain's ABCs when LangChain is importable."""
     from .cross_encoder import HuggingFaceCrossEncoder
     from .embeddings import HuggingFaceEmbeddings
     from .reranker import ScoredCrossEncoderReranker
+    from .retrievers import BM25Retriever, ContextualCompressionRetriever, EnsembleRetriever
     from .vectorstore import Milvus, PGVector
 
     out = dict(HuggingFaceEmbeddings=HuggingFaceEmbeddings, HuggingFaceCrossEncoder=HuggingFaceCrossEncoder,
-               ScoredCrossEncoderReranker=ScoredCrossEncoderReranker, Milvus=Milvus, PGVector=PGVector)
+               ScoredCrossEncoderReranker=ScoredCrossEncoderReranker, Milvus=Milvus, PGVector=PGVector,
+               BM25Retriever=BM25Retriever, EnsembleRetriever=EnsembleRetriever,
+               ContextualCompressionRetriever=ContextualCompressionRetriever)
     try:  # pragma: no cover - LangChain is not present in the build image
         from langchain_core.embeddings import Embeddings
         from langchain_core.vectorstores import VectorStore
@@ -76,6 +81,43 @@ def build_classes() -> Dict[str, Any]:
             ranked = sorted(zip(documents, scores), key=lambda ds: ds[1], reverse=True)
             return [copy_document(d, {**d.metadata, "relevance_score": s}) for d, s in ranked[: self.top_n]]
 
+    from langchain_core.retrievers import BaseRetriever
+    from .bm25 import BM25Index
+    from .retrievers import default_preprocessing_func
+
+    class LCBM25Retriever(BaseRetriever):  # type: ignore[misc]
+        """pydantic form of retrievers.BM25Retriever (GPU BM25Index behind langchain's BaseRetriever)."""
+        vectorizer: Any = None
+        docs: Any = None
+        k: int = 4
+        preprocess_func: Any = default_preprocessing_func
+        model_config = ConfigDict(arbitrary_types_allowed=True)
+
+        @classmethod
+        def from_texts(cls, texts, metadatas=None, bm25_params=None, preprocess_func=default_preprocessing_func, **kwargs):
+            from langchain_core.documents import Document as LCDocument
+            texts = list(texts)
+            vectorizer = BM25Index([preprocess_func(t) for t in texts], **(bm25_params or {}))
+            metadatas = metadatas or ({} for _ in texts)
+            docs = [LCDocument(page_content=t, metadata=m) for t, m in zip(texts, metadatas)]
+            return cls(vectorizer=vectorizer, docs=docs, preprocess_func=preprocess_func, **kwargs)
+
+        @classmethod
+        def from_documents(cls, documents, *, bm25_params=None, preprocess_func=default_preprocessing_func, **kwargs):
+            documents = list(documents)
+            return cls.from_texts([d.page_content for d in documents], [d.metadata for d in documents],
+                                  bm25_params=bm25_params, preprocess_func=preprocess_func, **kwargs)
+
+        def _get_relevant_documents(self, query, *, run_manager=None):
+            return self.vectorizer.get_top_n(self.preprocess_func(query), self.docs, n=self.k)
+
+    LCBM25Retriever.__name__ = "BM25Retriever"
+    out.update(BM25Retriever=LCBM25Retriever)
+    try:   # LangChain's own fusion / compression retrievers work unchanged over BaseRetriever objects
+        from langchain.retrievers import ContextualCompressionRetriever as LCC, EnsembleRetriever as LCE
+        out.update(EnsembleRetriever=LCE, ContextualCompressionRetriever=LCC)
+    except Exception:
+        pass
     LCReranker.__name__ = "ScoredCrossEncoderReranker"
     LCEmbeddings.__name__ = "HuggingFaceEmbeddings"
     out.update(HuggingFaceEmbeddings=LCEmbeddings, Milvus=_vs(Milvus), PGVector=_vs(PGVector),
@@ -105,5 +147,15 @@ def install() -> Dict[str, Any]:
     except Exception:
         _module("langchain_community.cross_encoders", HuggingFaceCrossEncoder=c["HuggingFaceCrossEncoder"])
     _module("ScoredCrossEncoderReranker", ScoredCrossEncoderReranker=c["ScoredCrossEncoderReranker"])
+    try:
+        import langchain_community.retrievers as lcr  # type: ignore  # pragma: no cover
+        lcr.BM25Retriever = c["BM25Retriever"]  # pragma: no cover
+    except Exception:
+        _module("langchain_community.retrievers", BM25Retriever=c["BM25Retriever"])
+    try:
+        import langchain.retrievers  # type: ignore  # noqa: F401  # pragma: no cover
+    except Exception:
+        _module("langchain.retrievers", EnsembleRetriever=c["EnsembleRetriever"],
+                ContextualCompressionRetriever=c["ContextualCompressionRetriever"])
     _installed = c
     return c

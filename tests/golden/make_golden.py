@@ -145,11 +145,41 @@ def flat_goldens():
     return out
 
 
+def bm25_goldens():
+    """BM25Okapi top-n (scores float64, document numbers) from the restatement in oracle/hybrid_ref.py — rank_bm25
+    itself is not installed in this image, so these pin the restatement against regressions only; the hand-worked
+    known-answer test lives in tests/test_hybrid_cpu.py."""
+    sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+    from cases import BM25_CASES, bm25_inputs
+    from oracle import hybrid_ref as H
+    out = {}
+    for case in BM25_CASES:
+        if case["n"] > 10000:
+            continue
+        corpus, queries = bm25_inputs(case)
+        bm = H.BM25Okapi(corpus)
+        k = case["k"]
+        ids = np.full((len(queries), k), -1, dtype=np.int64)
+        sc = np.zeros((len(queries), k), dtype=np.float64)
+        for qi, q in enumerate(queries):
+            s, d = H.bm25_topk(bm, q, k)
+            ids[qi, :len(d)] = d
+            sc[qi, :len(s)] = s
+        out[f"{case['name']}_ids"] = ids
+        out[f"{case['name']}_scores"] = sc
+    return out
+
+
 if __name__ == "__main__":
+    if "--bm25" in sys.argv:
+        np.savez_compressed(os.path.join(HERE, "bm25.npz"), **bm25_goldens())
+        print("bm25.npz", os.path.getsize(os.path.join(HERE, "bm25.npz")) // 1024, "KiB")
+        sys.exit(0)
     torch.manual_seed(0)
     torch.set_num_threads(8)
     np.savez_compressed(os.path.join(HERE, "encoder.npz"), **encoder_goldens())
     np.savez_compressed(os.path.join(HERE, "cross_encoder.npz"), **cross_encoder_goldens())
     np.savez_compressed(os.path.join(HERE, "flat.npz"), **flat_goldens())
-    for f in ("encoder.npz", "cross_encoder.npz", "flat.npz"):
+    np.savez_compressed(os.path.join(HERE, "bm25.npz"), **bm25_goldens())
+    for f in ("encoder.npz", "cross_encoder.npz", "flat.npz", "bm25.npz"):
         print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, "KiB")
