@@ -102,6 +102,44 @@ static int launch_mode(const SplitOperand& A, const SplitOperand& W, const GemmP
     return launch_bn<MODE, 128>(A, W, p, sms, st);
 }
 
+bool gemm_ln_supported(const SplitOperand& W, int N) {
+    static const int off = [] { const char* e = getenv("RMU_LN_FUSED"); return e ? atoi(e) == 0 : 0; }();
+    return !off && W.box64_rows == kWideBN && (N == 2 * kLnBN || N == 4 * kLnBN);
+}
+
+int launch_gemm_ln(const SplitOperand& A, const SplitOperand& W, const GemmLnParams& p, int sms, cudaStream_t st) {
+    if (p.M <= 0) return RMU_OK;
+    if (!gemm_ln_supported(W, p.N) || p.K % kGemmBK != 0 || A.cols != p.K || W.cols != p.K || W.rows < p.N || A.rows < p.M) {
+        set_error("launch_gemm_ln: shape not supported (N = 384 or 768, K % 64)");
+        return RMU_ERR_UNSUPPORTED;
+    }
+    static bool attr_set = false;
+    if (!attr_set) {
+        RMU_CUDA(cudaFuncSetAttribute(gemm_f16x3_ln_kernel<kGemmEpiWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kLnSmem)));
+        attr_set = true;
+    }
+    const int CL = p.N / kLnBN;
+    const int m_blks = (p.M + kGemmBM - 1) / kGemmBM;
+    const int clusters = std::max(1, std::min(m_blks, sms / CL));
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(static_cast<unsigned>(clusters * CL));
+    cfg.blockDim = dim3(kGemmThreads);
+    cfg.dynamicSmemBytes = kLnSmem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = static_cast<unsigned>(CL);
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    ProfScope _ps(PROF_GEMM, st);
+    RMU_CUDA(cudaLaunchKernelEx(&cfg, gemm_f16x3_ln_kernel<kGemmEpiWarps>, A.map_hi, A.map_lo, W.map192_hi, W.map192_lo, p));
+    count_launch();
+    RMU_CHECK_LAUNCH();
+    return RMU_OK;
+}
+
 int launch_gemm(int mode, const SplitOperand& A, const SplitOperand& W, const GemmParams& p, int sms, cudaStream_t st) {
     if (p.M <= 0) return RMU_OK;
     if (p.N % 128 != 0 || p.K % kGemmBK != 0 || A.cols != p.K || W.cols != p.K || W.rows < p.N || A.rows < p.M) {

@@ -619,6 +619,266 @@ gemm_f16x3_pair_kernel(const __grid_constant__ CUtensorMap tAh, const __grid_con
     if (warp == 1) tmem_dealloc_pair<512>(tmem_base);
 }
 
+// ---------------------------------------------------------------------------------------------------
+// GEMM + bias + residual + LayerNorm -> split planes in ONE kernel (attention-output and FFN-output
+// projections of a post-LN BERT block: transformers BertSelfOutput / BertOutput, modeling_bert.py:287-357).
+//
+// A LayerNorm row spans the whole N = hidden, i.e. CL = N / 192 output tiles.  The CL CTAs of a thread-block
+// CLUSTER take the CL column tiles of the same 128-row block at the same time; every epilogue warp computes
+// (mean, M2) of its 96 columns of y = acc + bias + residual per row, publishes them into the shared memory of
+// all CL CTAs (st.shared::cluster + a cluster-scope mbarrier), and each CTA combines the 2*CL partials per row
+// with Chan's parallel-variance formula (exact two-pass statistics, no E[x^2] - E[x]^2 cancellation).  y never
+// leaves the SM: it is written back into the TMEM accumulator columns between the passes.  Compared with
+// GEMM(RESID_F32) + ln_kernel this removes one fp32 write and one fp32 read of [M, N] per LayerNorm.
+// ---------------------------------------------------------------------------------------------------
+struct GemmLnParams {
+    int M, N, K;
+    const float* bias;                            // [N]
+    const __half* res_hi; const __half* res_lo;   // [M, N] residual stream (planes)
+    const float* gamma; const float* beta;        // [N]
+    float eps;
+    __half* out_hi; __half* out_lo;               // [M, N] LayerNorm output (planes)
+};
+
+constexpr int kLnBN = 192;
+constexpr int kLnMaxCL = 4;                       // hidden <= 768
+constexpr int kLnStages = 2;
+constexpr int kLnStageBytes = 2 * kGemmPlaneBytes + 2 * kLnBN * 128;
+constexpr size_t kLnStatsBytes = 2ull * (2 * kLnMaxCL) * kGemmBM * sizeof(float2);
+constexpr size_t kLnSmem = static_cast<size_t>(kLnStages) * kLnStageBytes + kGemmStagingBytes + kLnStatsBytes + 256 + 1024;
+
+template <int EPI_WARPS>      // = kGemmEpiWarps (two warps per TMEM lane quadrant, 96 columns each)
+__global__ void __launch_bounds__(64 + 32 * EPI_WARPS, 1)
+gemm_f16x3_ln_kernel(const __grid_constant__ CUtensorMap tAh, const __grid_constant__ CUtensorMap tAl,
+                     const __grid_constant__ CUtensorMap tWh, const __grid_constant__ CUtensorMap tWl,
+                     const GemmLnParams p) {
+    static_assert(EPI_WARPS == kGemmEpiWarps, "statistics exchange is laid out for two 96-column parts per CTA");
+    constexpr uint32_t IDESC = umma_idesc(0 /*f16*/, kGemmBM, kLnBN);
+    constexpr int kWPlane = kLnBN * 128;
+    constexpr int kPartCols = kLnBN / 2;          // columns per epilogue warp: 3 chunks of 32
+    extern __shared__ uint8_t gemm_smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(gemm_smem_raw) + 1023) & ~uintptr_t(1023));
+    float* staging = reinterpret_cast<float*>(smem + kLnStages * kLnStageBytes);
+    float2* stats = reinterpret_cast<float2*>(smem + kLnStages * kLnStageBytes + kGemmStagingBytes);   // [2][2*CLmax][128]
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + kLnStages * kLnStageBytes + kGemmStagingBytes + kLnStatsBytes);
+    uint64_t* empty = full + kLnStages;
+    uint64_t* acc_full = empty + kLnStages;
+    uint64_t* acc_empty = acc_full + 2;
+    uint64_t* stat_full = acc_empty + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(stat_full + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const unsigned lane = lane_id();
+    const uint32_t CL = cluster_nctarank();
+    const uint32_t rank = cluster_ctarank();
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < kLnStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&acc_full[i], 1);
+            mbar_init(&acc_empty[i], 32 * kGemmEpiWarps);
+            mbar_init(&stat_full[i], kGemmEpiWarps * CL);       // one arrival per epilogue warp of every CTA of the cluster
+        }
+        fence_mbar_init();
+        prefetch_tmap(&tAh); prefetch_tmap(&tAl); prefetch_tmap(&tWh); prefetch_tmap(&tWl);
+    }
+    if (warp == 1) tmem_alloc<512>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                           // every CTA's barriers exist before any remote arrive
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int m_blks = (p.M + kGemmBM - 1) / kGemmBM;
+    const int k_blks = p.K / kGemmBK;
+    const int cluster_id = blockIdx.x / CL, n_clusters = gridDim.x / CL;
+    const int nb = static_cast<int>(rank);        // this CTA's column tile of every row block
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int slot = 0;
+            uint32_t phase = 0;
+            for (int mb = cluster_id; mb < m_blks; mb += n_clusters) {
+                for (int kb = 0; kb < k_blks; ++kb) {
+                    mbar_wait(&empty[slot], phase ^ 1);
+                    uint8_t* st = smem + slot * kLnStageBytes;
+                    mbar_arrive_expect_tx(&full[slot], kLnStageBytes);
+                    tma_load_2d(st, &tAh, kb * kGemmBK, mb * kGemmBM, &full[slot], kEvictNormal);
+                    tma_load_2d(st + kGemmPlaneBytes, &tAl, kb * kGemmBK, mb * kGemmBM, &full[slot], kEvictNormal);
+                    tma_load_2d(st + 2 * kGemmPlaneBytes, &tWh, kb * kGemmBK, nb * kLnBN, &full[slot], kEvictLast);
+                    tma_load_2d(st + 2 * kGemmPlaneBytes + kWPlane, &tWl, kb * kGemmBK, nb * kLnBN, &full[slot], kEvictLast);
+                    if (++slot == kLnStages) { slot = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            int slot = 0;
+            uint32_t phase = 0;
+            int i = 0;
+            for (int mb = cluster_id; mb < m_blks; mb += n_clusters, ++i) {
+                const int buf = i & 1;
+                const uint32_t use = static_cast<uint32_t>(i >> 1);
+                mbar_wait(&acc_empty[buf], (use & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t d_addr = tmem_base + buf * kLnBN;
+                for (int kb = 0; kb < k_blks; ++kb) {
+                    mbar_wait(&full[slot], phase);
+                    tc_fence_after();
+                    const uint32_t sbase = smem_u32(smem + slot * kLnStageBytes);
+                    const uint64_t dAh = umma_desc_sw128_kmajor(sbase);
+                    const uint64_t dAl = umma_desc_sw128_kmajor(sbase + kGemmPlaneBytes);
+                    const uint64_t dWh = umma_desc_sw128_kmajor(sbase + 2 * kGemmPlaneBytes);
+                    const uint64_t dWl = umma_desc_sw128_kmajor(sbase + 2 * kGemmPlaneBytes + kWPlane);
+#pragma unroll
+                    for (int k = 0; k < kGemmBK / 16; ++k) {
+                        const uint64_t off = static_cast<uint64_t>(k * 2);
+                        mma_f16_ss(d_addr, dAh + off, dWh + off, IDESC, (kb | k) != 0 ? 1u : 0u);
+                        mma_f16_ss(d_addr, dAl + off, dWh + off, IDESC, 1u);
+                        mma_f16_ss(d_addr, dAh + off, dWl + off, IDESC, 1u);
+                    }
+                    tc_commit(&empty[slot]);
+                    if (++slot == kLnStages) { slot = 0; phase ^= 1; }
+                }
+                tc_commit(&acc_full[buf]);
+            }
+        }
+    } else {
+        // ---- epilogue warp (quad, chalf): rows quad*32 .. +32 of the tile (thread = row in TMEM), columns
+        //      chalf*96 .. +96 of the tile.  part = rank*2 + chalf identifies its 96-column slice of the LN row.
+        const int ew = warp - 2;
+        const int quad = warp & 3;
+        const int chalf = ew >> 2;
+        const int part = static_cast<int>(rank) * 2 + chalf;
+        const int nparts = 2 * static_cast<int>(CL);
+        float* stg = staging + ew * (32 * kGemmStageRow);
+        const int rsub = static_cast<int>(lane) >> 4, cp = (static_cast<int>(lane) & 15) * 2;
+        const int trow = quad * 32 + static_cast<int>(lane);           // this thread's row of the tile
+        const float inv_n = 1.0f / static_cast<float>(p.N);
+        int i = 0;
+        for (int mb = cluster_id; mb < m_blks; mb += n_clusters, ++i) {
+            const int buf = i & 1;
+            const uint32_t use = static_cast<uint32_t>(i >> 1);
+            mbar_wait(&acc_full[buf], use & 1);
+            tc_fence_after();
+            const int row_base = mb * kGemmBM + quad * 32;
+            // ---- pass A: y = acc + bias + residual (added in the coalesced column-pair layout through the staging
+            //      tile), row sums in the thread = row layout, y back into the accumulator columns
+            float sum = 0.f;
+#pragma unroll 1
+            for (int cc = 0; cc < 3; ++cc) {
+                const int c = chalf * 3 + cc;
+                const int col0 = nb * kLnBN + c * 32;
+                __half2 rsh[16], rsl[16];
+#pragma unroll
+                for (int q = 0; q < 16; ++q) {
+                    const int grow = row_base + 2 * q + rsub;
+                    if (grow < p.M) {
+                        const size_t o = static_cast<size_t>(grow) * p.N + col0 + cp;
+                        rsh[q] = *reinterpret_cast<const __half2*>(p.res_hi + o);
+                        rsl[q] = *reinterpret_cast<const __half2*>(p.res_lo + o);
+                    } else {
+                        rsh[q] = __float2half2_rn(0.f);
+                        rsl[q] = __float2half2_rn(0.f);
+                    }
+                }
+                const float2 bia2 = __ldg(reinterpret_cast<const float2*>(p.bias + col0 + cp));
+                uint32_t r[32];
+                const uint32_t taddr = tmem_addr(tmem_base, quad * 32, buf * kLnBN + c * 32);
+                tmem_ld32(taddr, r);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; ++j) stg[lane * kGemmStageRow + j] = __uint_as_float(r[j]);
+                __syncwarp();
+#pragma unroll
+                for (int rr = 0; rr < 32; rr += 2) {
+                    const int rl = rr + rsub;
+                    const float2 fh = __half22float2(rsh[rr >> 1]);
+                    const float2 fl = __half22float2(rsl[rr >> 1]);
+                    stg[rl * kGemmStageRow + cp] = stg[rl * kGemmStageRow + cp] + bia2.x + (fh.x + fl.x);
+                    stg[rl * kGemmStageRow + cp + 1] = stg[rl * kGemmStageRow + cp + 1] + bia2.y + (fh.y + fl.y);
+                }
+                __syncwarp();
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const float y = stg[lane * kGemmStageRow + j];
+                    sum += y;
+                    r[j] = __float_as_uint(y);
+                }
+                tmem_st32(taddr, r);
+                __syncwarp();
+            }
+            tmem_st_wait();
+            // ---- pass B: centred second moment of this warp's 96 columns
+            const float m_loc = sum * (1.0f / static_cast<float>(kPartCols));
+            float m2 = 0.f;
+#pragma unroll 1
+            for (int cc = 0; cc < 3; ++cc) {
+                uint32_t r[32];
+                tmem_ld32(tmem_addr(tmem_base, quad * 32, buf * kLnBN + (chalf * 3 + cc) * 32), r);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; ++j) { const float d = __uint_as_float(r[j]) - m_loc; m2 = fmaf(d, d, m2); }
+            }
+            // ---- exchange (mean, M2) of (row, part) with every CTA of the cluster
+            const int sbuf = i & 1;
+            float2* my = stats + (static_cast<size_t>(sbuf) * (2 * kLnMaxCL) + part) * kGemmBM + trow;
+            for (uint32_t c = 0; c < CL; ++c) st_cluster_f2(my, c, make_float2(m_loc, m2));
+            __syncwarp();
+            if (lane == 0) for (uint32_t c = 0; c < CL; ++c) mbar_arrive_cluster(&stat_full[sbuf], c);
+            mbar_wait_cluster(&stat_full[sbuf], use & 1);
+            float mean = 0.f;
+            for (int q = 0; q < nparts; ++q) mean += stats[(static_cast<size_t>(sbuf) * (2 * kLnMaxCL) + q) * kGemmBM + trow].x;
+            mean /= static_cast<float>(nparts);
+            float M2 = 0.f;
+            for (int q = 0; q < nparts; ++q) {
+                const float2 s2 = stats[(static_cast<size_t>(sbuf) * (2 * kLnMaxCL) + q) * kGemmBM + trow];
+                const float d = s2.x - mean;
+                M2 += s2.y + static_cast<float>(kPartCols) * d * d;
+            }
+            const float rstd = 1.0f / sqrtf(M2 * inv_n + p.eps);
+            // ---- pass C: normalise, gamma / beta in the column-pair layout, split, coalesced plane stores
+#pragma unroll 1
+            for (int cc = 0; cc < 3; ++cc) {
+                const int c = chalf * 3 + cc;
+                const int col0 = nb * kLnBN + c * 32;
+                const float2 g2 = __ldg(reinterpret_cast<const float2*>(p.gamma + col0 + cp));
+                const float2 b2 = __ldg(reinterpret_cast<const float2*>(p.beta + col0 + cp));
+                uint32_t r[32];
+                tmem_ld32(tmem_addr(tmem_base, quad * 32, buf * kLnBN + c * 32), r);
+                tmem_ld_wait();
+                if (cc == 2) {                       // last TMEM read of this warp for the tile
+                    tc_fence_before();
+                    mbar_arrive(&acc_empty[buf]);
+                }
+#pragma unroll
+                for (int j = 0; j < 32; ++j) stg[lane * kGemmStageRow + j] = (__uint_as_float(r[j]) - mean) * rstd;
+                __syncwarp();
+#pragma unroll
+                for (int rr = 0; rr < 32; rr += 2) {
+                    const int rl = rr + rsub;
+                    const int grow = row_base + rl;
+                    if (grow < p.M) {
+                        const float a = stg[rl * kGemmStageRow + cp] * g2.x + b2.x;
+                        const float b = stg[rl * kGemmStageRow + cp + 1] * g2.y + b2.y;
+                        const size_t o = static_cast<size_t>(grow) * p.N + col0 + cp;
+                        __half h0, l0, h1, l1;
+                        split_f16(a, h0, l0);
+                        split_f16(b, h1, l1);
+                        *reinterpret_cast<__half2*>(p.out_hi + o) = __halves2half2(h0, h1);
+                        *reinterpret_cast<__half2*>(p.out_lo + o) = __halves2half2(l0, l1);
+                    }
+                }
+                __syncwarp();
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (warp == 1) tmem_dealloc<512>(tmem_base);
+    cluster_sync_all();                           // no CTA leaves while a peer could still address its shared memory
+}
+
 // A K-major fp16 operand carried as two planes, with the TMA maps of both
 struct SplitOperand {
     __half* hi = nullptr;
@@ -638,5 +898,8 @@ struct SplitOperand {
 int make_split_operand(SplitOperand* op, __half* hi, __half* lo, int64_t rows, int cols, bool is_activation);
 // C = A * W^T with the epilogue `mode`; A rows used = p.M (<= A.rows)
 int launch_gemm(int mode, const SplitOperand& A, const SplitOperand& W, const GemmParams& p, int sms, cudaStream_t st);
+// fused GEMM + bias + residual + LayerNorm -> planes; supported when N is 384 or 768 (gemm_ln_supported)
+bool gemm_ln_supported(const SplitOperand& W, int N);
+int launch_gemm_ln(const SplitOperand& A, const SplitOperand& W, const GemmLnParams& p, int sms, cudaStream_t st);
 
 }  // namespace rmu
