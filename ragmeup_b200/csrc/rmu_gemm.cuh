@@ -84,7 +84,9 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tAh, const __grid_constant
     constexpr size_t kStagingBytes = static_cast<size_t>(kEpi) * 32 * kGemmStageRow * sizeof(float);
     static_assert(static_cast<size_t>(kGemmStages) * kGemmStageBytes + kStagingBytes + 256 + 1024 <= kGemmSmem, "smem budget");
     extern __shared__ uint8_t gemm_smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(gemm_smem_raw) + 1023) & ~uintptr_t(1023));
+    // 1024-byte alignment by OFFSET into the shared array: a pointer round-trip through an integer would lose the
+    // shared address space and turn every staging access into a generic LD/ST
+    uint8_t* smem = gemm_smem_raw + ((1024u - (smem_u32(gemm_smem_raw) & 1023u)) & 1023u);
     float* staging = reinterpret_cast<float*>(smem + kGemmStages * kGemmStageBytes);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + kGemmStages * kGemmStageBytes + kStagingBytes);
     uint64_t* empty = full + kGemmStages;
@@ -272,7 +274,9 @@ gemm_f16x3_wide_kernel(const __grid_constant__ CUtensorMap tAh, const __grid_con
     constexpr int kWideWBytes = 128 * kRowBytes;               // one W plane of a stage
     constexpr int kWideStageBytes = 2 * kWideABytes + 2 * kWideWBytes;
     extern __shared__ uint8_t gemm_smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(gemm_smem_raw) + 1023) & ~uintptr_t(1023));
+    // 1024-byte alignment by OFFSET into the shared array: a pointer round-trip through an integer would lose the
+    // shared address space and turn every staging access into a generic LD/ST
+    uint8_t* smem = gemm_smem_raw + ((1024u - (smem_u32(gemm_smem_raw) & 1023u)) & 1023u);
     float* staging = reinterpret_cast<float*>(smem + kWideStages * kWideStageBytes);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + kWideStages * kWideStageBytes + kGemmStagingBytes);
     uint64_t* empty = full + kWideStages;
@@ -458,7 +462,9 @@ gemm_f16x3_pair_kernel(const __grid_constant__ CUtensorMap tAh, const __grid_con
                        const GemmParams p) {
     constexpr uint32_t IDESC = umma_idesc(0 /*f16*/, 256, kPairBN);
     extern __shared__ uint8_t gemm_smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(gemm_smem_raw) + 1023) & ~uintptr_t(1023));
+    // 1024-byte alignment by OFFSET into the shared array: a pointer round-trip through an integer would lose the
+    // shared address space and turn every staging access into a generic LD/ST
+    uint8_t* smem = gemm_smem_raw + ((1024u - (smem_u32(gemm_smem_raw) & 1023u)) & 1023u);
     float* staging = reinterpret_cast<float*>(smem + kPairStages * kPairStageBytes);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + kPairStages * kPairStageBytes + kGemmStagingBytes);
     uint64_t* empty = full + kPairStages;
@@ -657,7 +663,9 @@ gemm_f16x3_ln_kernel(const __grid_constant__ CUtensorMap tAh, const __grid_const
     constexpr int kWPlane = kLnBN * 128;
     constexpr int kPartCols = kLnBN / 2;          // columns per epilogue warp: 3 chunks of 32
     extern __shared__ uint8_t gemm_smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(gemm_smem_raw) + 1023) & ~uintptr_t(1023));
+    // 1024-byte alignment by OFFSET into the shared array: a pointer round-trip through an integer would lose the
+    // shared address space and turn every staging access into a generic LD/ST
+    uint8_t* smem = gemm_smem_raw + ((1024u - (smem_u32(gemm_smem_raw) & 1023u)) & 1023u);
     float* staging = reinterpret_cast<float*>(smem + kLnStages * kLnStageBytes);
     float2* stats = reinterpret_cast<float2*>(smem + kLnStages * kLnStageBytes + kGemmStagingBytes);   // [2][2*CLmax][128]
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + kLnStages * kLnStageBytes + kGemmStagingBytes + kLnStatsBytes);
@@ -754,71 +762,80 @@ gemm_f16x3_ln_kernel(const __grid_constant__ CUtensorMap tAh, const __grid_const
         const int rsub = static_cast<int>(lane) >> 4, cp = (static_cast<int>(lane) & 15) * 2;
         const int trow = quad * 32 + static_cast<int>(lane);           // this thread's row of the tile
         const float inv_n = 1.0f / static_cast<float>(p.N);
+        // residual rows of chunk (chalf*3 + cc), coalesced: lane = column pair, 16 row pairs
+        auto load_res = [&](int row_base_, int cc_, __half2 (&h)[16], __half2 (&l)[16]) {
+            const int col0_ = nb * kLnBN + (chalf * 3 + cc_) * 32;
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+                const int grow = row_base_ + 2 * q + rsub;
+                if (grow < p.M) {
+                    const size_t o = static_cast<size_t>(grow) * p.N + col0_ + cp;
+                    h[q] = *reinterpret_cast<const __half2*>(p.res_hi + o);
+                    l[q] = *reinterpret_cast<const __half2*>(p.res_lo + o);
+                } else {
+                    h[q] = __float2half2_rn(0.f);
+                    l[q] = __float2half2_rn(0.f);
+                }
+            }
+        };
         int i = 0;
+        __half2 rsh[16], rsl[16];
+        if (cluster_id < m_blks) load_res(cluster_id * kGemmBM + quad * 32, 0, rsh, rsl);
         for (int mb = cluster_id; mb < m_blks; mb += n_clusters, ++i) {
             const int buf = i & 1;
             const uint32_t use = static_cast<uint32_t>(i >> 1);
-            mbar_wait(&acc_full[buf], use & 1);
-            tc_fence_after();
             const int row_base = mb * kGemmBM + quad * 32;
-            // ---- pass A: y = acc + bias + residual (added in the coalesced column-pair layout through the staging
-            //      tile), row sums in the thread = row layout, y back into the accumulator columns
-            float sum = 0.f;
-#pragma unroll 1
+            // ---- pass A: y = acc + (bias + residual).  The residual chunk is loaded coalesced (lane = column pair,
+            //      one chunk ahead; the first chunk of a row block is fetched during the previous block's pass C), parked with the bias in the
+            //      staging tile, and picked up in the thread = row layout next to the tcgen05.ld registers; y goes back
+            //      into the accumulator columns and the statistics of this warp's 96 columns are formed from registers
+            //      (per-chunk mean / M2, chunks merged with Chan's formula).
+            float m_loc = 0.f, m2 = 0.f;
+#pragma unroll
             for (int cc = 0; cc < 3; ++cc) {
                 const int c = chalf * 3 + cc;
                 const int col0 = nb * kLnBN + c * 32;
-                __half2 rsh[16], rsl[16];
-#pragma unroll
-                for (int q = 0; q < 16; ++q) {
-                    const int grow = row_base + 2 * q + rsub;
-                    if (grow < p.M) {
-                        const size_t o = static_cast<size_t>(grow) * p.N + col0 + cp;
-                        rsh[q] = *reinterpret_cast<const __half2*>(p.res_hi + o);
-                        rsl[q] = *reinterpret_cast<const __half2*>(p.res_lo + o);
-                    } else {
-                        rsh[q] = __float2half2_rn(0.f);
-                        rsl[q] = __float2half2_rn(0.f);
-                    }
-                }
                 const float2 bia2 = __ldg(reinterpret_cast<const float2*>(p.bias + col0 + cp));
-                uint32_t r[32];
-                const uint32_t taddr = tmem_addr(tmem_base, quad * 32, buf * kLnBN + c * 32);
-                tmem_ld32(taddr, r);
-                tmem_ld_wait();
-#pragma unroll
-                for (int j = 0; j < 32; ++j) stg[lane * kGemmStageRow + j] = __uint_as_float(r[j]);
-                __syncwarp();
 #pragma unroll
                 for (int rr = 0; rr < 32; rr += 2) {
                     const int rl = rr + rsub;
                     const float2 fh = __half22float2(rsh[rr >> 1]);
                     const float2 fl = __half22float2(rsl[rr >> 1]);
-                    stg[rl * kGemmStageRow + cp] = stg[rl * kGemmStageRow + cp] + bia2.x + (fh.x + fl.x);
-                    stg[rl * kGemmStageRow + cp + 1] = stg[rl * kGemmStageRow + cp + 1] + bia2.y + (fh.y + fl.y);
+                    stg[rl * kGemmStageRow + cp] = bia2.x + (fh.x + fl.x);
+                    stg[rl * kGemmStageRow + cp + 1] = bia2.y + (fh.y + fl.y);
                 }
+                if (cc < 2) load_res(row_base, cc + 1, rsh, rsl);      // in flight during the rest of this chunk
                 __syncwarp();
+                if (cc == 0) {
+                    mbar_wait(&acc_full[buf], use & 1);
+                    tc_fence_after();
+                }
+                uint32_t r[32];
+                const uint32_t taddr = tmem_addr(tmem_base, quad * 32, buf * kLnBN + c * 32);
+                tmem_ld32(taddr, r);
+                tmem_ld_wait();
+                float s = 0.f;
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
-                    const float y = stg[lane * kGemmStageRow + j];
-                    sum += y;
+                    const float y = __uint_as_float(r[j]) + stg[lane * kGemmStageRow + j];
                     r[j] = __float_as_uint(y);
+                    s += y;
                 }
                 tmem_st32(taddr, r);
-                __syncwarp();
+                __syncwarp();                                            // staging tile free for the next chunk
+                const float mc = s * (1.0f / 32.0f);
+                float qc = 0.f;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) { const float d = __uint_as_float(r[j]) - mc; qc = fmaf(d, d, qc); }
+                // merge (32 * cc columns: m_loc, m2) with (32 columns: mc, qc)
+                const float na = 32.0f * static_cast<float>(cc), nn = na + 32.0f;
+                const float delta = mc - m_loc;
+                m_loc += delta * (32.0f / nn);
+                m2 += qc + delta * delta * (na * 32.0f / nn);
             }
             tmem_st_wait();
-            // ---- pass B: centred second moment of this warp's 96 columns
-            const float m_loc = sum * (1.0f / static_cast<float>(kPartCols));
-            float m2 = 0.f;
-#pragma unroll 1
-            for (int cc = 0; cc < 3; ++cc) {
-                uint32_t r[32];
-                tmem_ld32(tmem_addr(tmem_base, quad * 32, buf * kLnBN + (chalf * 3 + cc) * 32), r);
-                tmem_ld_wait();
-#pragma unroll
-                for (int j = 0; j < 32; ++j) { const float d = __uint_as_float(r[j]) - m_loc; m2 = fmaf(d, d, m2); }
-            }
+            // first residual chunk of the NEXT row block: in flight during the exchange and pass C
+            if (mb + n_clusters < m_blks) load_res((mb + n_clusters) * kGemmBM + quad * 32, 0, rsh, rsl);
             // ---- exchange (mean, M2) of (row, part) with every CTA of the cluster
             const int sbuf = i & 1;
             float2* my = stats + (static_cast<size_t>(sbuf) * (2 * kLnMaxCL) + part) * kGemmBM + trow;

@@ -270,7 +270,9 @@ scan_tf32_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
     static_assert(BN * NBUF <= 512 - kScanACols, "accumulators must fit beside the query block in TMEM");
 
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    // 1024-byte alignment by OFFSET into the shared array: a pointer round-trip through an integer would lose the
+    // shared address space and turn every staging access into a generic LD/ST
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* slabs = smem;
     float* stage = reinterpret_cast<float*>(smem + NSLAB * SLAB_BYTES);          // [32][128] epilogue staging
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + NSLAB * SLAB_BYTES + 32 * 128 * sizeof(float));
