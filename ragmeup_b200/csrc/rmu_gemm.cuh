@@ -632,7 +632,7 @@ gemm_f16x3_pair_kernel(const __grid_constant__ CUtensorMap tAh, const __grid_con
 // A LayerNorm row spans the whole N = hidden, i.e. CL = N / 192 output tiles.  The CL CTAs of a thread-block
 // CLUSTER take the CL column tiles of the same 128-row block at the same time; every epilogue warp computes
 // (mean, M2) of its 96 columns of y = acc + bias + residual per row, publishes them into the shared memory of
-// all CL CTAs (st.shared::cluster + a cluster-scope mbarrier), and each CTA combines the 2*CL partials per row
+// all CL CTAs (st.async whose completion bytes are credited to the destination CTA's mbarrier), and each CTA combines the 2*CL partials per row
 // with Chan's parallel-variance formula (exact two-pass statistics, no E[x^2] - E[x]^2 cancellation).  y never
 // leaves the SM: it is written back into the TMEM accumulator columns between the passes.  Compared with
 // GEMM(RESID_F32) + ln_kernel this removes one fp32 write and one fp32 read of [M, N] per LayerNorm.
@@ -651,7 +651,8 @@ constexpr int kLnMaxCL = 4;                       // hidden <= 768
 constexpr int kLnStages = 2;
 constexpr int kLnStageBytes = 2 * kGemmPlaneBytes + 2 * kLnBN * 128;
 constexpr size_t kLnStatsBytes = 2ull * (2 * kLnMaxCL) * kGemmBM * sizeof(float2);
-constexpr size_t kLnSmem = static_cast<size_t>(kLnStages) * kLnStageBytes + kGemmStagingBytes + kLnStatsBytes + 256 + 1024;
+constexpr size_t kLnVecBytes = 3 * kLnBN * sizeof(float);      // this CTA's bias | gamma | beta columns
+constexpr size_t kLnSmem = static_cast<size_t>(kLnStages) * kLnStageBytes + kGemmStagingBytes + kLnStatsBytes + kLnVecBytes + 256 + 1024;
 
 template <int EPI_WARPS>      // = kGemmEpiWarps (two warps per TMEM lane quadrant, 96 columns each)
 __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, 1)
@@ -668,7 +669,10 @@ gemm_f16x3_ln_kernel(const __grid_constant__ CUtensorMap tAh, const __grid_const
     uint8_t* smem = gemm_smem_raw + ((1024u - (smem_u32(gemm_smem_raw) & 1023u)) & 1023u);
     float* staging = reinterpret_cast<float*>(smem + kLnStages * kLnStageBytes);
     float2* stats = reinterpret_cast<float2*>(smem + kLnStages * kLnStageBytes + kGemmStagingBytes);   // [2][2*CLmax][128]
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + kLnStages * kLnStageBytes + kGemmStagingBytes + kLnStatsBytes);
+    // bias | gamma | beta of this CTA's 192 columns: the cluster-scope acquire of every tile invalidates L1, so
+    // re-reading them from global memory would miss each time
+    float* svec = reinterpret_cast<float*>(smem + kLnStages * kLnStageBytes + kGemmStagingBytes + kLnStatsBytes);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + kLnStages * kLnStageBytes + kGemmStagingBytes + kLnStatsBytes + kLnVecBytes);
     uint64_t* empty = full + kLnStages;
     uint64_t* acc_full = empty + kLnStages;
     uint64_t* acc_empty = acc_full + 2;
@@ -684,12 +688,18 @@ gemm_f16x3_ln_kernel(const __grid_constant__ CUtensorMap tAh, const __grid_const
         for (int i = 0; i < 2; ++i) {
             mbar_init(&acc_full[i], 1);
             mbar_init(&acc_empty[i], 32 * kGemmEpiWarps);
-            mbar_init(&stat_full[i], kGemmEpiWarps * CL);       // one arrival per epilogue warp of every CTA of the cluster
+            mbar_init(&stat_full[i], 1);                        // armed per tile with the bytes of all 2*CL column slices
         }
         fence_mbar_init();
         prefetch_tmap(&tAh); prefetch_tmap(&tAl); prefetch_tmap(&tWh); prefetch_tmap(&tWl);
     }
     if (warp == 1) tmem_alloc<512>(tmem_slot);
+    for (int j = threadIdx.x; j < kLnBN; j += blockDim.x) {
+        const int col = static_cast<int>(cluster_ctarank()) * kLnBN + j;
+        svec[j] = p.bias[col];
+        svec[kLnBN + j] = p.gamma[col];
+        svec[2 * kLnBN + j] = p.beta[col];
+    }
     tc_fence_before();
     __syncthreads();
     cluster_sync_all();                           // every CTA's barriers exist before any remote arrive
@@ -795,7 +805,7 @@ gemm_f16x3_ln_kernel(const __grid_constant__ CUtensorMap tAh, const __grid_const
             for (int cc = 0; cc < 3; ++cc) {
                 const int c = chalf * 3 + cc;
                 const int col0 = nb * kLnBN + c * 32;
-                const float2 bia2 = __ldg(reinterpret_cast<const float2*>(p.bias + col0 + cp));
+                const float2 bia2 = *reinterpret_cast<const float2*>(svec + c * 32 + cp);
 #pragma unroll
                 for (int rr = 0; rr < 32; rr += 2) {
                     const int rl = rr + rsub;
@@ -839,10 +849,9 @@ gemm_f16x3_ln_kernel(const __grid_constant__ CUtensorMap tAh, const __grid_const
             // ---- exchange (mean, M2) of (row, part) with every CTA of the cluster
             const int sbuf = i & 1;
             float2* my = stats + (static_cast<size_t>(sbuf) * (2 * kLnMaxCL) + part) * kGemmBM + trow;
-            for (uint32_t c = 0; c < CL; ++c) st_cluster_f2(my, c, make_float2(m_loc, m2));
-            __syncwarp();
-            if (lane == 0) for (uint32_t c = 0; c < CL; ++c) mbar_arrive_cluster(&stat_full[sbuf], c);
-            mbar_wait_cluster(&stat_full[sbuf], use & 1);
+            if (ew == 0 && lane == 0) mbar_arrive_expect_tx(&stat_full[sbuf], static_cast<uint32_t>(kGemmBM * nparts * sizeof(float2)));
+            for (uint32_t c = 0; c < CL; ++c) st_async_cluster_f2(my, &stat_full[sbuf], c, make_float2(m_loc, m2));
+            mbar_wait(&stat_full[sbuf], use & 1);
             float mean = 0.f;
             for (int q = 0; q < nparts; ++q) mean += stats[(static_cast<size_t>(sbuf) * (2 * kLnMaxCL) + q) * kGemmBM + trow].x;
             mean /= static_cast<float>(nparts);
@@ -858,8 +867,8 @@ gemm_f16x3_ln_kernel(const __grid_constant__ CUtensorMap tAh, const __grid_const
             for (int cc = 0; cc < 3; ++cc) {
                 const int c = chalf * 3 + cc;
                 const int col0 = nb * kLnBN + c * 32;
-                const float2 g2 = __ldg(reinterpret_cast<const float2*>(p.gamma + col0 + cp));
-                const float2 b2 = __ldg(reinterpret_cast<const float2*>(p.beta + col0 + cp));
+                const float2 g2 = *reinterpret_cast<const float2*>(svec + kLnBN + c * 32 + cp);
+                const float2 b2 = *reinterpret_cast<const float2*>(svec + 2 * kLnBN + c * 32 + cp);
                 uint32_t r[32];
                 tmem_ld32(tmem_addr(tmem_base, quad * 32, buf * kLnBN + c * 32), r);
                 tmem_ld_wait();

@@ -216,6 +216,18 @@ __device__ __forceinline__ void st_cluster_f2(float2* p, uint32_t cta, float2 v)
         ::"r"(smem_u32(p)), "r"(cta), "f"(v.x), "f"(v.y)
         : "memory");
 }
+// 8-byte asynchronous store into CTA `cta`'s shared memory whose completion is credited (8 bytes of transaction
+// count) to the mbarrier at `bar`'s offset in THAT CTA: data and signal travel together, no release fence and no
+// separate remote arrive (the waiter sees the data once the barrier phase completes, as with TMA)
+__device__ __forceinline__ void st_async_cluster_f2(float2* p, uint64_t* bar, uint32_t cta, float2 v) {
+    asm volatile(
+        "{\n\t.reg .b32 ra, rb;\n\t"
+        "mapa.shared::cluster.u32 ra, %0, %2;\n\t"
+        "mapa.shared::cluster.u32 rb, %1, %2;\n\t"
+        "st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f32 [ra], {%3, %4}, [rb];\n\t}"
+        ::"r"(smem_u32(p)), "r"(smem_u32(bar)), "r"(cta), "f"(v.x), "f"(v.y)
+        : "memory");
+}
 __device__ __forceinline__ uint32_t cluster_nctarank() {
     uint32_t r;
     asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));

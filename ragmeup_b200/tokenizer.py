@@ -12,6 +12,7 @@ batches into the ragged ``cu_seqlens`` layout the CUDA encoder consumes
 from __future__ import annotations
 
 import os
+from itertools import chain
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
@@ -126,14 +127,11 @@ def encode_ragged(tok: Tokenizer, texts_a: Sequence[str], texts_b: Optional[Sequ
 
 
 def _pack(enc) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
-    lens = np.fromiter((len(e.ids) for e in enc), dtype=np.int64, count=len(enc))
+    id_lists = [e.ids for e in enc]                      # each .ids builds a Python list: fetch it once
+    lens = np.fromiter(map(len, id_lists), dtype=np.int64, count=len(id_lists))
     cu = np.zeros(len(enc) + 1, dtype=np.int32)
     np.cumsum(lens, out=cu[1:])
     total = int(cu[-1])
-    ids = np.empty(total, dtype=np.int32)
-    typ = np.empty(total, dtype=np.int32)
-    for e, o in zip(enc, cu[:-1]):
-        n = len(e.ids)
-        ids[o:o + n] = e.ids
-        typ[o:o + n] = e.type_ids
+    ids = np.fromiter(chain.from_iterable(id_lists), dtype=np.int32, count=total)
+    typ = np.fromiter(chain.from_iterable(e.type_ids for e in enc), dtype=np.int32, count=total)
     return ids, typ, cu

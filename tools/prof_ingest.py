@@ -28,11 +28,20 @@ def main():
     db.add_documents(docs[:1000], ids=[d.metadata["id"] for d in docs[:1000]])      # warm-up
     db = Milvus.from_documents([], emb, drop_old=True, connection_args={"uri": "x.db"}, collection_name="c")
     torch.cuda.synchronize()
+    prof = None
+    if os.environ.get("PROF_CPROFILE") == "1":
+        import cProfile
+        prof = cProfile.Profile()
+        prof.enable()
     t0 = time.time()
     for a in range(0, n, 1000):
         db.add_documents(docs[a:a + 1000], ids=[d.metadata["id"] for d in docs[a:a + 1000]])
     torch.cuda.synchronize()
     dt = time.time() - t0
+    if prof is not None:
+        import pstats
+        prof.disable()
+        pstats.Stats(prof).sort_stats("cumulative").print_stats(18)
     print(f"add_documents: {n} docs in {dt:.2f}s = {n / dt:.0f} docs/s ({n / dt * cu[-1] / 2000:.0f} tokens/s), "
           f"store rows {len(db)}", flush=True)
     t0 = time.time()

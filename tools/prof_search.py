@@ -21,3 +21,10 @@ for it in range(IT):
     ts.append(e0.elapsed_time(e1))
 print(f"variant={os.environ.get('RMU_SCAN_VARIANT','0')} N={N} Q={Q} k={K} {metric}: ms per search {['%.3f' % t for t in ts]}  "
       f"{4.0*N*D/(min(ts)*1e-3)/1e9:.0f} GB/s D={D}", flush=True)
+if os.environ.get("PROF_CLASSES") == "1":
+    from ragmeup_b200 import _lib
+    _lib.profile_enable(True); _lib.profile_reset()
+    for _ in range(10): ix.search(qs, K, mode=MODE_AUTO)
+    torch.cuda.synchronize()
+    print({k: (round(v[0] / 10, 4), v[1] // 10) for k, v in _lib.profile_read().items() if v[1]}, flush=True)
+    _lib.profile_enable(False)
