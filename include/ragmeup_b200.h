@@ -124,6 +124,18 @@ int rmu_bm25_search(rmu_bm25* h, const int32_t* q_ptr, const int32_t* q_terms, i
 int rmu_bm25_search_host(rmu_bm25* h, const int32_t* q_ptr_h, const int32_t* q_terms_h, int Q, int k,
                          double* out_scores_h, int64_t* out_ids_h, void* stream);
 
+/* Host-only helper (no GPU work): the inverted index rank_bm25 would build from
+ * `[text.split() for text in texts]` (BM25Retriever.from_texts, server/RAGHelper.py:436-443) — Python
+ * str.split() whitespace semantics on UTF-8, vocabulary ids in first-seen order, postings CSR by term
+ * with documents ascending.  texts_utf8[i] has text_bytes[i] bytes (no terminator needed). */
+typedef struct rmu_bm25_csr rmu_bm25_csr;
+int rmu_bm25_csr_build(const char* const* texts_utf8, const int64_t* text_bytes, int64_t n_docs, rmu_bm25_csr** out);
+int rmu_bm25_csr_sizes(const rmu_bm25_csr* c, int64_t* n_terms, int64_t* nnz, int64_t* vocab_bytes);
+/* doc_len [n_docs], post_ptr [n_terms+1], post_doc/post_tf [nnz], vocab_off [n_terms+1], vocab_bytes */
+int rmu_bm25_csr_export(const rmu_bm25_csr* c, int64_t* doc_len, int64_t* post_ptr, int32_t* post_doc,
+                        int32_t* post_tf, int64_t* vocab_off, char* vocab_bytes);
+int rmu_bm25_csr_free(rmu_bm25_csr* c);
+
 /* ------------------------------------------------------------------ BERT encoder
  * Stands behind HuggingFaceEmbeddings.embed_documents/embed_query (sentence-transformers
  * encode -> BertModel -> Pooling -> Normalize) and HuggingFaceCrossEncoder.score

@@ -62,6 +62,11 @@ SIGNATURES = {
                                   C.c_void_p]),
     "rmu_bm25_search_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                        C.c_void_p]),
+    "rmu_bm25_csr_build": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_void_p)]),
+    "rmu_bm25_csr_sizes": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "rmu_bm25_csr_export": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                      C.c_void_p]),
+    "rmu_bm25_csr_free": (C.c_int, [C.c_void_p]),
     "rmu_encoder_create": (C.c_int, [C.POINTER(BertConfigC), C.POINTER(C.c_void_p), C.c_int, C.c_int,
                                      C.POINTER(C.c_void_p)]),
     "rmu_encoder_destroy": (None, [C.c_void_p]),

@@ -46,19 +46,25 @@ class InvertedIndex:
                 ent_term.append(tid)
                 ent_tf.append(f)
             ent_cnt[i] = len(freq)
-        self.corpus_size = n
-        self.avgdl = num_doc / self.corpus_size        # ZeroDivisionError on an empty corpus, as rank_bm25
-        self.doc_len = doc_len
-        n_terms = len(vocab)
         terms = np.asarray(ent_term, dtype=np.int64)
         tfs = np.asarray(ent_tf, dtype=np.int32)
         docs = np.repeat(np.arange(n, dtype=np.int32), ent_cnt)
+        n_terms = len(vocab)
         df = np.bincount(terms, minlength=n_terms).astype(np.int64)
         order = np.argsort(terms, kind="stable")       # documents stay ascending inside a term
         self.post_ptr = np.zeros(n_terms + 1, dtype=np.int64)
         np.cumsum(df, out=self.post_ptr[1:])
         self.post_doc = np.ascontiguousarray(docs[order])
         self.post_tf = np.ascontiguousarray(tfs[order])
+        self.doc_len = doc_len
+        self._set_statistics()
+
+    def _set_statistics(self) -> None:
+        """avgdl, idf (with the epsilon floor) and the document-length denominators from doc_len / post_ptr, with the
+        operations and the summation order of rank_bm25 (``_initialize`` / ``_calc_idf`` / ``get_scores``)."""
+        n = self.corpus_size = len(self.doc_len)
+        self.avgdl = int(self.doc_len.sum()) / self.corpus_size      # ZeroDivisionError on an empty corpus, as rank_bm25
+        df = np.diff(self.post_ptr)
         # _calc_idf: sequential float64 sum in vocabulary (first-seen) order
         idf = [math.log(n - int(f) + 0.5) - math.log(int(f) + 0.5) for f in df]
         idf_sum = 0.0
@@ -68,7 +74,50 @@ class InvertedIndex:
         eps = self.epsilon * self.average_idf
         self.idf = np.asarray([eps if v < 0 else v for v in idf], dtype=np.float64)
         # document-length part of the denominator, numpy float64 exactly as get_scores evaluates it
-        self.den = np.ascontiguousarray(self.k1 * (1 - self.b + self.b * doc_len / self.avgdl), dtype=np.float64)
+        self.den = np.ascontiguousarray(self.k1 * (1 - self.b + self.b * self.doc_len / self.avgdl), dtype=np.float64)
+
+    @classmethod
+    def from_texts(cls, texts: Sequence[str], k1: float = 1.5, b: float = 0.75, epsilon: float = 0.25, **kw):
+        """Index of ``[t.split() for t in texts]`` built by the C++ host routine ``rmu_bm25_csr_build`` (Python
+        ``str.split()`` semantics, first-seen vocabulary order): same arrays as ``cls([t.split() for t in texts])``."""
+        try:
+            enc = [t.encode("utf-8") for t in texts]
+        except UnicodeEncodeError:                      # lone surrogates: only the Python path can represent them
+            return cls([t.split() for t in texts], k1, b, epsilon, **kw)
+        self = cls.__new__(cls)
+        self._prepare(**kw)
+        self.k1, self.b, self.epsilon = float(k1), float(b), float(epsilon)
+        n = len(enc)
+        lib = _lib.lib()
+        ptrs = (C.c_char_p * max(n, 1))(*enc)
+        lens = np.asarray([len(e) for e in enc], dtype=np.int64)
+        h = C.c_void_p()
+        _lib.check(lib.rmu_bm25_csr_build(C.cast(ptrs, C.c_void_p), lens.ctypes.data, n, C.byref(h)), "rmu_bm25_csr_build")
+        try:
+            nt, nnz, vb = C.c_int64(), C.c_int64(), C.c_int64()
+            _lib.check(lib.rmu_bm25_csr_sizes(h, C.byref(nt), C.byref(nnz), C.byref(vb)), "rmu_bm25_csr_sizes")
+            self.doc_len = np.empty(n, dtype=np.int64)
+            self.post_ptr = np.empty(nt.value + 1, dtype=np.int64)
+            self.post_doc = np.empty(nnz.value, dtype=np.int32)
+            self.post_tf = np.empty(nnz.value, dtype=np.int32)
+            voff = np.empty(nt.value + 1, dtype=np.int64)
+            vbytes = C.create_string_buffer(max(vb.value, 1))
+            _lib.check(lib.rmu_bm25_csr_export(h, self.doc_len.ctypes.data, self.post_ptr.ctypes.data,
+                                               self.post_doc.ctypes.data, self.post_tf.ctypes.data, voff.ctypes.data,
+                                               C.cast(vbytes, C.c_void_p)), "rmu_bm25_csr_export")
+        finally:
+            lib.rmu_bm25_csr_free(h)
+        raw = vbytes.raw
+        self.vocab = {raw[voff[i]:voff[i + 1]].decode("utf-8"): i for i in range(nt.value)}
+        self._set_statistics()
+        self._finish()
+        return self
+
+    def _prepare(self, **kw) -> None:      # hooks for the GPU subclass
+        pass
+
+    def _finish(self) -> None:
+        pass
 
     def term_ids(self, query: Sequence[str]) -> List[int]:
         """query tokens -> ids of the terms that contribute (``(self.idf.get(q) or 0)``: unknown terms and terms whose
@@ -84,14 +133,17 @@ class InvertedIndex:
 class BM25Index(InvertedIndex):
     def __init__(self, corpus: Sequence[Sequence[str]], k1: float = 1.5, b: float = 0.75, epsilon: float = 0.25,
                  device: Optional[int] = None):
-        self._bind_device(device)
+        self._prepare(device=device)
         super().__init__(corpus, k1, b, epsilon)
-        self._upload()
+        self._finish()
 
-    def _bind_device(self, device: Optional[int]) -> None:
+    def _prepare(self, device: Optional[int] = None, **_) -> None:
         torch = _lib.require_cuda()
         self.torch = torch
         self.device = torch.device("cuda", torch.cuda.current_device() if device is None else device)
+
+    def _finish(self) -> None:
+        self._upload()
 
     @classmethod
     def from_arrays(cls, post_ptr: np.ndarray, post_doc: np.ndarray, post_tf: np.ndarray, doc_len: np.ndarray,
@@ -99,26 +151,15 @@ class BM25Index(InvertedIndex):
         """Index over PRE-TOKENISED data: postings CSR by integer term id (documents ascending inside a term) and
         document lengths; statistics are derived exactly as in ``InvertedIndex`` (vocabulary = ``str(term id)``)."""
         self = cls.__new__(cls)
-        self._bind_device(device)
+        self._prepare(device=device)
         self.k1, self.b, self.epsilon = float(k1), float(b), float(epsilon)
         self.post_ptr = np.ascontiguousarray(post_ptr, dtype=np.int64)
         self.post_doc = np.ascontiguousarray(post_doc, dtype=np.int32)
         self.post_tf = np.ascontiguousarray(post_tf, dtype=np.int32)
         self.doc_len = np.ascontiguousarray(doc_len, dtype=np.int64)
-        n, n_terms = len(self.doc_len), len(self.post_ptr) - 1
-        self.corpus_size = n
-        self.vocab = {str(t): t for t in range(n_terms)}
-        self.avgdl = int(self.doc_len.sum()) / n
-        df = np.diff(self.post_ptr)
-        idf = [math.log(n - int(f) + 0.5) - math.log(int(f) + 0.5) for f in df]
-        idf_sum = 0.0
-        for v in idf:
-            idf_sum += v
-        self.average_idf = idf_sum / len(idf) if idf else 0.0
-        eps = self.epsilon * self.average_idf
-        self.idf = np.asarray([eps if v < 0 else v for v in idf], dtype=np.float64)
-        self.den = np.ascontiguousarray(self.k1 * (1 - self.b + self.b * self.doc_len / self.avgdl), dtype=np.float64)
-        self._upload()
+        self.vocab = {str(t): t for t in range(len(self.post_ptr) - 1)}
+        self._set_statistics()
+        self._finish()
         return self
 
     def _upload(self) -> None:

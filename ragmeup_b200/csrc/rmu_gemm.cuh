@@ -804,7 +804,6 @@ gemm_f16x3_ln_kernel(const __grid_constant__ CUtensorMap tAh, const __grid_const
 #pragma unroll
             for (int cc = 0; cc < 3; ++cc) {
                 const int c = chalf * 3 + cc;
-                const int col0 = nb * kLnBN + c * 32;
                 const float2 bia2 = *reinterpret_cast<const float2*>(svec + c * 32 + cp);
 #pragma unroll
                 for (int rr = 0; rr < 32; rr += 2) {

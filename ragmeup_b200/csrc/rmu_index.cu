@@ -242,7 +242,8 @@ struct ScanParams {
     int ntiles;            // ceil(n / BN)
     const float* rscale;   // nullable (cosine)
     const float* rbias;    // nullable (L2)
-    unsigned long long* lists;  // [gridDim.x][128][2*KEEP]
+    unsigned long long* lists;  // [gridDim.x][128][CAP]: unsorted candidates of (CTA, query), counts[] of them valid
+    int* counts;                // [gridDim.x][128]
     float* dbg;            // diagnostics: CTA 0 dumps the raw accumulators of its first tile [128][BN]
     int ablate;            // profiling only: bit0 skip MMA issue, bit1 skip epilogue work, bit2 skip TMEM loads
     // threshold exchange: phase 0 = whole range, thresholds start at -inf; phase 1 = only the first `lead`
@@ -279,7 +280,8 @@ scan_tf32_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
     uint64_t* empty = full + NSLAB;
     uint64_t* acc_full = empty + NSLAB;
     uint64_t* acc_empty = acc_full + NBUF;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + NBUF);
+    uint64_t* a_ready = acc_empty + NBUF;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_ready + 1);
 
     const int warp = threadIdx.x >> 5;
     const unsigned lane = lane_id();
@@ -288,6 +290,7 @@ scan_tf32_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
     if (threadIdx.x == 0) {
         for (int i = 0; i < NSLAB; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
         for (int i = 0; i < NBUF; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 128); }
+        mbar_init(a_ready, 128);
         fence_mbar_init();
         prefetch_tmap(&tmap);
     }
@@ -307,20 +310,21 @@ scan_tf32_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
     if (warp >= 2) {
         const int qi = quad * 32 + lane;
         const float* qrow = (qi < p.nq) ? p.q + static_cast<long long>(p.q0 + qi) * p.dim : nullptr;
+        // dim % 4 == 0 and 16-byte aligned rows (checked by the host): two float4 loads per 8 columns
         for (int c = 0; c < KB * 4; ++c) {
             uint32_t r[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const int d = c * 8 + j;
-                r[j] = (qrow != nullptr && d < p.kdim) ? __float_as_uint(qrow[p.kcol0 + d]) : 0u;
-            }
+            const int d = c * 8;
+            float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
+            if (qrow != nullptr && d < p.kdim) v0 = *reinterpret_cast<const float4*>(qrow + p.kcol0 + d);
+            if (qrow != nullptr && d + 4 < p.kdim) v1 = *reinterpret_cast<const float4*>(qrow + p.kcol0 + d + 4);
+            r[0] = __float_as_uint(v0.x); r[1] = __float_as_uint(v0.y); r[2] = __float_as_uint(v0.z); r[3] = __float_as_uint(v0.w);
+            r[4] = __float_as_uint(v1.x); r[5] = __float_as_uint(v1.y); r[6] = __float_as_uint(v1.z); r[7] = __float_as_uint(v1.w);
             tmem_st8(tmem_addr(tmem_base, quad * 32, c * 8), r);
         }
         tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(a_ready);                      // the MMA issuer waits for all 128 query rows; TMA streams meanwhile
     }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
 
     if (warp == 0) {
         // =========================== TMA producer ===========================
@@ -350,6 +354,8 @@ scan_tf32_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
         if (lane == 0) {
             int slot = 0;
             uint32_t phase = 0;
+            mbar_wait(a_ready, 0);                 // query block is in TMEM
+            tc_fence_after();
             for (int t = t0; t < t1; ++t) {
                 const int i = t - t0;
                 const int buf = i % NBUF;
@@ -470,10 +476,18 @@ scan_tf32_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
                 mbar_arrive(&acc_empty[buf]);
             }
         }
-        // final: every list sorted descending, zero padded to KEEP entries
+        // final: the list stays as it is (unsorted, <= CAP entries, a superset of this CTA's KEEP best above the
+        // threshold); the selection kernels read `counts` entries.  (Sorting 128 lists per CTA here, one lane at a
+        // time, was a fixed ~0.1 ms tail on every launch: it dominated 1M-row shards.)
+        // Long lists (KEEP >= 128) are still sorted and cut to KEEP here: reading 2 * KEEP entries of every CTA in the
+        // 8-pass radix select of finalize would cost more than it saves.
         if (p.kpass != 1) {
-            warp_compact<KEEP, CAP>(mybuf, cnt, tau, true);
-            for (int e = cnt; e < KEEP; ++e) mybuf[e] = 0ull;
+            if (KEEP >= 128) {
+                warp_compact<KEEP, CAP>(mybuf, cnt, tau, true);
+                for (int e = cnt; e < KEEP; ++e) mybuf[e] = 0ull;
+            } else {
+                p.counts[blockIdx.x * kScanQ + qi] = cnt;
+            }
         }
     }
 
@@ -570,6 +584,10 @@ __global__ void __launch_bounds__(256) exact_scan_kernel(const ExactParams p) {
     }
 }
 
+// threads of the selection kernels (select_tau, finalize): their 8 radix passes over nlists * len keys are latency-bound,
+// one CTA per query
+constexpr int kSelThreads = 512;
+
 // Block-wide radix select (8 bits per pass, most significant first): returns the ksel-th largest non-zero
 // key among load_key(0..total), or 1 ("keep everything") when fewer than ksel exist.  All threads call.
 template <typename LoadKey>
@@ -609,7 +627,8 @@ __device__ __forceinline__ unsigned long long block_radix_select(LoadKey load_ke
 
 // per-query global threshold for phase 2 of the scan: score of the keep-th best key over all CTAs'
 // phase-1 lists (-inf when fewer than keep candidates exist yet)
-__global__ void __launch_bounds__(256) select_tau_kernel(const unsigned long long* __restrict__ lists, int nlists, int lstride,
+__global__ void __launch_bounds__(kSelThreads) select_tau_kernel(const unsigned long long* __restrict__ lists,
+                                                         const int* __restrict__ counts, int nlists, int lstride,
                                                          int len, int keep, int q0, float* __restrict__ tau0) {
     __shared__ int hist[256];
     __shared__ unsigned long long s_prefix;
@@ -620,7 +639,7 @@ __global__ void __launch_bounds__(256) select_tau_kernel(const unsigned long lon
     auto load_key = [&](long long idx) -> unsigned long long {
         const long long l = idx >> len_shift;
         const int e = static_cast<int>(idx & (len - 1));
-        return lists[(l * kScanQ + f) * lstride + e];
+        return e < counts[l * kScanQ + f] ? lists[(l * kScanQ + f) * lstride + e] : 0ull;
     };
     const unsigned long long T = block_radix_select(load_key, total, keep, hist, &s_prefix, &s_remaining);
     if (threadIdx.x == 0) tau0[q0 + f] = (T <= 1ull) ? -INFINITY : key_score(T);
@@ -634,7 +653,8 @@ struct FinalizeParams {
     int nlists;        // lists per query
     int qstride;       // queries per list block (128 for the tensor scan, nq_total for the exact scan)
     int lstride;       // entries between consecutive queries' lists
-    int len;           // sorted valid (zero padded) entries per list, pow2
+    int len;           // entries read per list, pow2 (zero padded, or bounded by counts[])
+    const int* counts; // nullable: valid entries of list (l, query slot) = counts[l * qstride + slot]
     int ksel;          // candidates to select (<= 1024, <= len for a valid certificate)
     const float* x; long long n; int dim; int metric;
     const float* q;    // [nq_total, dim]
@@ -651,7 +671,7 @@ struct FinalizeParams {
     int* flags;        // [nq_total] 1 = certificate failed
 };
 
-__global__ void __launch_bounds__(256) finalize_kernel(const FinalizeParams p) {
+__global__ void __launch_bounds__(kSelThreads) finalize_kernel(const FinalizeParams p) {
     __shared__ unsigned long long cand[1024];
     __shared__ float cval[1024];
     __shared__ int hist[256];
@@ -680,6 +700,7 @@ __global__ void __launch_bounds__(256) finalize_kernel(const FinalizeParams p) {
     auto load_key = [&](long long idx) -> unsigned long long {
         const long long l = idx >> len_shift;
         const int e = static_cast<int>(idx & (p.len - 1));
+        if (p.counts != nullptr && e >= p.counts[l * p.qstride + qslot]) return 0ull;
         return p.lists[(l * p.qstride + qslot) * p.lstride + e];
     };
 
@@ -976,7 +997,7 @@ static int keep_for_k(int k) {
 template <int BN, int NBUF, int NSLAB, int KD, bool TMA3D, int KEEP>
 static int launch_scan(const CUtensorMap& tmap, const ScanParams& p, int grid, cudaStream_t st) {
     auto kern = scan_tf32_kernel<BN, NBUF, NSLAB, KD, TMA3D, KEEP>;
-    const size_t smem = static_cast<size_t>(NSLAB) * BN * 128 * KD + 32 * 128 * sizeof(float) + (2 * NSLAB + 2 * NBUF) * 8 + 16 + 1024;
+    const size_t smem = static_cast<size_t>(NSLAB) * BN * 128 * KD + 32 * 128 * sizeof(float) + (2 * NSLAB + 2 * NBUF + 1) * 8 + 16 + 1024;
     static bool attr_set = false;
     if (!attr_set) {
         RMU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
@@ -1142,7 +1163,9 @@ int rmu_index_search(rmu_index* idx, const float* queries, int nq, int k, int64_
     const int D = idx->dim;
     const long long N = idx->n;
     // tensor scan eligibility: TMA row pitch multiple of 16 B, query block fits TMEM, enough rows, k small
+    // (queries must be 16-byte aligned: the scan loads them as float4)
     const bool tensor_ok = (D % 4 == 0) && D <= 2 * kScanACols && N >= 16384 && k <= 128 && mode != RMU_SEARCH_EXACT &&
+                           (reinterpret_cast<uintptr_t>(queries) & 15) == 0 &&
                            (D <= kScanACols || !scan_3d());   // the K-split passes use the 2-D tensor map
     const bool ksplit = tensor_ok && D > kScanACols;
     const int keep = keep_for_k(k);                       // tensor: candidates kept per query (>= 3k)
@@ -1158,6 +1181,7 @@ int rmu_index_search(rmu_index* idx, const float* queries, int nq, int k, int64_
     const size_t o_nsel = carve(sizeof(int) * 4);
     const size_t o_scan = tensor_ok ? carve(sizeof(unsigned long long) * grid_scan * kScanQ * 2 * keep) : 0;
     const size_t o_tau = carve(sizeof(float) * nq);
+    const size_t o_cnt = tensor_ok ? carve(sizeof(int) * grid_scan * kScanQ) : 0;
     const long long npad = (N + 31) / 32 * 32;
     const size_t o_part = ksplit ? carve(sizeof(float) * kScanQ * static_cast<size_t>(npad)) : 0;
     const size_t o_exact = carve(sizeof(unsigned long long) * std::max(nchunks, 1) * static_cast<size_t>(nq) * keepx);
@@ -1170,6 +1194,7 @@ int rmu_index_search(rmu_index* idx, const float* queries, int nq, int k, int64_
     unsigned long long* d_scan = reinterpret_cast<unsigned long long*>(ws + o_scan);
     unsigned long long* d_exact = reinterpret_cast<unsigned long long*>(ws + o_exact);
     float* d_tau0 = reinterpret_cast<float*>(ws + o_tau);
+    int* d_cnt = reinterpret_cast<int*>(ws + o_cnt);
     float* d_part = reinterpret_cast<float*>(ws + o_part);
 
     const size_t qsmem = static_cast<size_t>(D) * sizeof(float);
@@ -1182,7 +1207,7 @@ int rmu_index_search(rmu_index* idx, const float* queries, int nq, int k, int64_
         fp.x = idx->x; fp.n = 0; fp.dim = D; fp.metric = idx->metric; fp.q = queries; fp.q0 = 0; fp.exact = 1;
         fp.k = k; fp.id_offset = id_offset; fp.max_norm_bits = idx->max_norm_bits; fp.eps_rel = 0.f;
         fp.out_scores = out_scores; fp.out_ids = reinterpret_cast<long long*>(out_ids); fp.flags = nullptr;
-        finalize_kernel<<<nq, 256, qsmem, st>>>(fp);
+        finalize_kernel<<<nq, kSelThreads, qsmem, st>>>(fp);
         count_launch();
         RMU_CHECK_LAUNCH();
         RMU_CUDA(cudaEventRecord(idx->ws_done, st));
@@ -1230,7 +1255,7 @@ int rmu_index_search(rmu_index* idx, const float* queries, int nq, int k, int64_
             sp.q = queries; sp.q0 = q0; sp.nq = std::min(kScanQ, nq - q0); sp.dim = D; sp.n = N; sp.ntiles = ntiles;
             sp.rscale = (idx->metric == RMU_METRIC_COSINE && !unit_rows) ? idx->rscale : nullptr;
             sp.rbias = (idx->metric == RMU_METRIC_L2 && !unit_rows) ? idx->rbias : nullptr;
-            sp.lists = d_scan;
+            sp.lists = d_scan; sp.counts = d_cnt;
             { static const char* ab = getenv("RMU_SCAN_ABLATE"); sp.ablate = ab ? atoi(ab) : 0; }
             const int grid = std::min(grid_scan, ntiles);
             // threshold exchange (big corpora): a cheap lead pass (first ~1 % of every CTA's tiles, KEEP = 32)
@@ -1248,7 +1273,7 @@ int rmu_index_search(rmu_index* idx, const float* queries, int nq, int k, int64_
                 rc = scan_launch(kLeadKeep, sp, grid);
                 if (rc != RMU_OK) return rc;
                 { ProfScope _ps(PROF_FINALIZE, st);
-                select_tau_kernel<<<sp.nq, 256, 0, st>>>(d_scan, grid, scan_cap(kLeadKeep), kLeadKeep, keep, q0, d_tau0); }
+                select_tau_kernel<<<sp.nq, kSelThreads, 0, st>>>(d_scan, d_cnt, grid, scan_cap(kLeadKeep), scan_cap(kLeadKeep), keep, q0, d_tau0); }
                 count_launch();
                 RMU_CHECK_LAUNCH();
                 sp.phase = 2;
@@ -1260,14 +1285,16 @@ int rmu_index_search(rmu_index* idx, const float* queries, int nq, int k, int64_
                 if (rc != RMU_OK) return rc;
             }
             FinalizeParams fp{};
-            fp.lists = d_scan; fp.nlists = grid; fp.qstride = kScanQ; fp.lstride = 2 * keep; fp.len = keep; fp.ksel = keep;
+            fp.lists = d_scan; fp.nlists = grid; fp.qstride = kScanQ; fp.lstride = scan_cap(keep); fp.ksel = keep;
+            if (keep >= 128) { fp.counts = nullptr; fp.len = keep; }            // sorted, cut to keep, zero padded
+            else { fp.counts = d_cnt; fp.len = scan_cap(keep); }                // raw lists + counts
             fp.x = idx->x; fp.n = N; fp.dim = D; fp.metric = idx->metric; fp.q = queries; fp.q0 = q0; fp.exact = 0;
             fp.unit_rows = unit_rows ? 1 : 0;
             fp.k = k; fp.id_offset = id_offset; fp.max_norm_bits = idx->max_norm_bits;
             fp.eps_rel = 2.2e-3f;   // > 2^-9: both TF32 operands truncated to 10 mantissa bits
             fp.out_scores = out_scores; fp.out_ids = reinterpret_cast<long long*>(out_ids); fp.flags = d_flags;
             { ProfScope _ps(PROF_FINALIZE, st);
-            finalize_kernel<<<sp.nq, 256, qsmem, st>>>(fp); }
+            finalize_kernel<<<sp.nq, kSelThreads, qsmem, st>>>(fp); }
             count_launch();
             RMU_CHECK_LAUNCH();
         }
@@ -1303,7 +1330,7 @@ int rmu_index_search(rmu_index* idx, const float* queries, int nq, int k, int64_
         fp.k = k; fp.id_offset = id_offset; fp.max_norm_bits = idx->max_norm_bits; fp.eps_rel = 0.f;
         fp.out_scores = out_scores; fp.out_ids = reinterpret_cast<long long*>(out_ids); fp.flags = nullptr;
         { ProfScope _ps(PROF_EXACT, st);
-        finalize_kernel<<<nq, 256, qsmem, st>>>(fp); }
+        finalize_kernel<<<nq, kSelThreads, qsmem, st>>>(fp); }
         count_launch();
         RMU_CHECK_LAUNCH();
     }
@@ -1329,7 +1356,8 @@ int rmu_debug_scan_tile(rmu_index* idx, const float* queries, int nq, float* out
     }
     std::lock_guard<std::mutex> g(idx->mu);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    int rc = ensure_ws(idx, sizeof(unsigned long long) * kScanQ * 2 * 64 + 1024);
+    const size_t dbg_lists = sizeof(unsigned long long) * kScanQ * 2 * 64;
+    int rc = ensure_ws(idx, dbg_lists + sizeof(int) * kScanQ + 1024);
     if (rc != RMU_OK) return rc;
     if (scan_3d()) rc = make_tmap_rows_kblocks(&idx->tmap, idx->x, static_cast<uint64_t>(idx->n), idx->dim / 32, scan_bn(), scan_kd());
     else rc = make_tmap_2d(&idx->tmap, idx->x, static_cast<uint64_t>(idx->n), static_cast<uint64_t>(idx->dim),
@@ -1339,7 +1367,9 @@ int rmu_debug_scan_tile(rmu_index* idx, const float* queries, int nq, float* out
     idx->tmap_bn = scan_bn();
     ScanParams sp{};
     sp.q = queries; sp.q0 = 0; sp.nq = nq; sp.dim = idx->dim; sp.n = idx->n; sp.ntiles = 1;
-    sp.lists = static_cast<unsigned long long*>(idx->ws); sp.dbg = out; sp.kcol0 = 0; sp.kdim = idx->dim; sp.kpass = 0;
+    sp.lists = static_cast<unsigned long long*>(idx->ws);
+    sp.counts = reinterpret_cast<int*>(static_cast<uint8_t*>(idx->ws) + dbg_lists);
+    sp.dbg = out; sp.kcol0 = 0; sp.kdim = idx->dim; sp.kpass = 0;
     return dispatch_scan(64, idx->tmap, sp, 1, st);
 }
 

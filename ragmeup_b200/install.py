@@ -97,7 +97,10 @@ def build_classes() -> Dict[str, Any]:
         def from_texts(cls, texts, metadatas=None, bm25_params=None, preprocess_func=default_preprocessing_func, **kwargs):
             from langchain_core.documents import Document as LCDocument
             texts = list(texts)
-            vectorizer = BM25Index([preprocess_func(t) for t in texts], **(bm25_params or {}))
+            if preprocess_func is default_preprocessing_func:
+                vectorizer = BM25Index.from_texts(texts, **(bm25_params or {}))
+            else:
+                vectorizer = BM25Index([preprocess_func(t) for t in texts], **(bm25_params or {}))
             metadatas = metadatas or ({} for _ in texts)
             docs = [LCDocument(page_content=t, metadata=m) for t, m in zip(texts, metadatas)]
             return cls(vectorizer=vectorizer, docs=docs, preprocess_func=preprocess_func, **kwargs)

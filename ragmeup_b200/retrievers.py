@@ -54,8 +54,10 @@ class BM25Retriever(_Retriever):
                    preprocess_func: Callable[[str], List[str]] = default_preprocessing_func,
                    **kwargs: Any) -> "BM25Retriever":
         texts = list(texts)
-        texts_processed = [preprocess_func(t) for t in texts]
-        vectorizer = BM25Index(texts_processed, **(bm25_params or {}))
+        if preprocess_func is default_preprocessing_func:
+            vectorizer = BM25Index.from_texts(texts, **(bm25_params or {}))     # str.split() + counting in C++
+        else:
+            vectorizer = BM25Index([preprocess_func(t) for t in texts], **(bm25_params or {}))
         metadatas = metadatas or ({} for _ in texts)
         docs = [Document(page_content=t, metadata=m) for t, m in zip(texts, metadatas)]
         return cls(vectorizer=vectorizer, docs=docs, preprocess_func=preprocess_func, **kwargs)

@@ -169,3 +169,52 @@ def test_similarity_provenance_oracle_known_answer():
     assert np.allclose(got, [x / sum(raw) for x in raw], atol=1e-7) and abs(sum(got) - 1) < 1e-6
     only_answer = P.compute_similarity(enc, "qry", ["d0", "d2"], "ans", include_query=False)
     assert np.allclose(only_answer, [1.0, 0.0])
+
+
+_WS = [" ", "\t", "\n", "\x0b", "\x0c", "\r", "\x1c", "\x1d", "\x1e", "\x1f", "\x85", "\xa0", " ", " ", " ",
+       " ", " ", " ", " ", " ", "　", "  \t "]
+_WORDS = ["a", "bb", "héllo", "日本語", "x​y", "naïve", "\U0001F600", "tab", "q" * 40, "́acc",
+          "zero\x00nul", "\x1bESC", "A", "a", "¡", "⁠wj", "﻿bom"]
+
+
+def _check_same_index(texts):
+    a = InvertedIndex([t.split() for t in texts])
+    b = InvertedIndex.from_texts(texts)
+    assert a.vocab == b.vocab
+    for name in ("post_ptr", "post_doc", "post_tf", "doc_len", "idf", "den"):
+        assert np.array_equal(getattr(a, name), getattr(b, name)), name
+    assert a.avgdl == b.avgdl and a.average_idf == b.average_idf
+
+
+def test_cpp_index_builder_equals_python_split_and_count():
+    """rmu_bm25_csr_build (host C++): Python str.split() semantics on UTF-8 incl. every str.isspace() code point,
+    NUL bytes, zero-width characters that are NOT whitespace, empty / all-blank documents; first-seen vocabulary."""
+    rng = np.random.default_rng(0)
+    texts = []
+    for _ in range(1500):
+        t = _WS[int(rng.integers(len(_WS)))] if rng.random() < 0.3 else ""
+        for _ in range(int(rng.integers(0, 30))):
+            t += _WORDS[int(rng.integers(len(_WORDS)))] + _WS[int(rng.integers(len(_WS)))]
+        texts.append(t)
+    texts += ["", "   ", "　　", "single", "trailing ", " leading"]
+    _check_same_index(texts)
+    # every whitespace code point Python knows, against every neighbouring non-space code point class
+    spaces = [chr(c) for c in range(0x3001) if chr(c).isspace()]
+    assert len(spaces) == 29
+    _check_same_index(["x" + s + "y" + s + s + "x" for s in spaces] + ["p​q ᠎ r s"])
+    # lone surrogates cannot be UTF-8 encoded: the Python path takes over
+    odd = InvertedIndex.from_texts(["ok \ud800 fine", "fine"])
+    assert set(odd.vocab) == {"ok", "\ud800", "fine"}
+
+
+def test_cpp_index_builder_property():
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=60, deadline=None)
+    @given(st.lists(st.text(alphabet=st.characters(blacklist_categories=("Cs",)), max_size=40), min_size=1, max_size=12))
+    def prop(texts):
+        if not any(t.split() for t in texts):
+            texts = texts + ["w"]
+        _check_same_index(texts)
+
+    prop()
