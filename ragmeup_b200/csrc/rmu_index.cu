@@ -588,15 +588,19 @@ __global__ void __launch_bounds__(256) exact_scan_kernel(const ExactParams p) {
 // one CTA per query
 constexpr int kSelThreads = 512;
 
-// Block-wide radix select (8 bits per pass, most significant first): returns the ksel-th largest non-zero
-// key among load_key(0..total), or 1 ("keep everything") when fewer than ksel exist.  All threads call.
+// Block-wide radix select (8 bits per pass, most significant first) over passes [pass0, pass1): after pass 8 the
+// state holds the ksel-th largest non-zero key among load_key(0..total); after pass 4 its 32 score bits (the low
+// word still zero) and, in *s_ties, how many keys share those score bits.  *s_remaining < 0 means fewer than ksel
+// keys exist ("keep everything").  pass0 == 0 initialises the state.  All threads call.
 template <typename LoadKey>
-__device__ __forceinline__ unsigned long long block_radix_select(LoadKey load_key, long long total, int ksel, int* hist,
-                                                                 unsigned long long* s_prefix, int* s_remaining) {
+__device__ __forceinline__ void block_radix_passes(LoadKey load_key, long long total, int ksel, int pass0, int pass1, int* hist,
+                                                   unsigned long long* s_prefix, int* s_remaining, int* s_ties) {
     const int tid = threadIdx.x;
-    if (tid == 0) { *s_prefix = 0ull; *s_remaining = ksel; }
-    __syncthreads();
-    for (int pass = 0; pass < 8; ++pass) {
+    if (pass0 == 0) {
+        if (tid == 0) { *s_prefix = 0ull; *s_remaining = ksel; *s_ties = 0; }
+        __syncthreads();
+    }
+    for (int pass = pass0; pass < pass1; ++pass) {
         const int shift = 56 - 8 * pass;
         for (int i = tid; i < 256; i += blockDim.x) hist[i] = 0;
         __syncthreads();
@@ -618,10 +622,21 @@ __device__ __forceinline__ unsigned long long block_radix_select(LoadKey load_ke
                 rem -= hist[b];
             }
             if (b < 0) { *s_remaining = -1; }
-            else { *s_prefix = prefix | (static_cast<unsigned long long>(b) << shift); *s_remaining = rem; }
+            else { *s_prefix = prefix | (static_cast<unsigned long long>(b) << shift); *s_remaining = rem; *s_ties = hist[b]; }
         }
         __syncthreads();
     }
+}
+
+// the ksel-th largest non-zero key, or 1 ("keep everything") when fewer than ksel exist.  Ties on the 32 score bits
+// are rare: when the keys that share the selected score are all needed (s_ties == s_remaining after four passes) the
+// threshold is that score with a zero row word and the four passes over the row bits are skipped.
+template <typename LoadKey>
+__device__ __forceinline__ unsigned long long block_radix_select(LoadKey load_key, long long total, int ksel, int* hist,
+                                                                 unsigned long long* s_prefix, int* s_remaining, int* s_ties) {
+    block_radix_passes(load_key, total, ksel, 0, 4, hist, s_prefix, s_remaining, s_ties);
+    if (*s_remaining >= 0 && *s_ties != *s_remaining)        // uniform: shared state, read after the barrier
+        block_radix_passes(load_key, total, ksel, 4, 8, hist, s_prefix, s_remaining, s_ties);
     return *s_remaining < 0 ? 1ull : *s_prefix;
 }
 
@@ -632,7 +647,7 @@ __global__ void __launch_bounds__(kSelThreads) select_tau_kernel(const unsigned 
                                                          int len, int keep, int q0, float* __restrict__ tau0) {
     __shared__ int hist[256];
     __shared__ unsigned long long s_prefix;
-    __shared__ int s_remaining;
+    __shared__ int s_remaining, s_ties;
     const int f = blockIdx.x;
     const long long total = static_cast<long long>(nlists) * len;
     const int len_shift = __ffs(len) - 1;
@@ -641,8 +656,8 @@ __global__ void __launch_bounds__(kSelThreads) select_tau_kernel(const unsigned 
         const int e = static_cast<int>(idx & (len - 1));
         return e < counts[l * kScanQ + f] ? lists[(l * kScanQ + f) * lstride + e] : 0ull;
     };
-    const unsigned long long T = block_radix_select(load_key, total, keep, hist, &s_prefix, &s_remaining);
-    if (threadIdx.x == 0) tau0[q0 + f] = (T <= 1ull) ? -INFINITY : key_score(T);
+    block_radix_passes(load_key, total, keep, 0, 4, hist, &s_prefix, &s_remaining, &s_ties);   // the score bits suffice
+    if (threadIdx.x == 0) tau0[q0 + f] = s_remaining < 0 ? -INFINITY : key_score(s_prefix);
 }
 
 // =====================================================================================================
@@ -678,7 +693,7 @@ __global__ void __launch_bounds__(kSelThreads) finalize_kernel(const FinalizePar
     __shared__ float red[32];
     __shared__ int s_ncand;
     __shared__ unsigned long long s_prefix;
-    __shared__ int s_remaining;
+    __shared__ int s_remaining, s_ties;
     extern __shared__ float qs[];  // [dim]
 
     const int f = blockIdx.x;
@@ -704,7 +719,7 @@ __global__ void __launch_bounds__(kSelThreads) finalize_kernel(const FinalizePar
         return p.lists[(l * p.qstride + qslot) * p.lstride + e];
     };
 
-    const unsigned long long T = block_radix_select(load_key, total, p.ksel, hist, &s_prefix, &s_remaining);
+    const unsigned long long T = block_radix_select(load_key, total, p.ksel, hist, &s_prefix, &s_remaining, &s_ties);
     if (tid == 0) s_ncand = 0;
     __syncthreads();
     // ---- collect keys >= T
