@@ -113,18 +113,23 @@ int launch_gemm_ln(const SplitOperand& A, const SplitOperand& W, const GemmLnPar
         set_error("launch_gemm_ln: shape not supported (N = 384 or 768, K % 64)");
         return RMU_ERR_UNSUPPORTED;
     }
-    static bool attr_set = false;
-    if (!attr_set) {
-        RMU_CUDA(cudaFuncSetAttribute(gemm_f16x3_ln_kernel<kGemmEpiWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kLnSmem)));
-        attr_set = true;
-    }
     const int CL = p.N / kLnBN;
+    // three epilogue warps per TMEM lane quadrant when the projection is short (K <= 512: its epilogue, not its MMAs,
+    // bounds it: 158 -> 145 us at K = 384) and the cluster is a pair (shared-memory budget); RMU_LN_EPI = 8 | 12 forces
+    static const int epi_env = [] { const char* e = getenv("RMU_LN_EPI"); return e ? atoi(e) : 0; }();
+    const bool epi12 = CL == 2 && (epi_env == 12 || (epi_env == 0 && p.K <= 512));
+    static bool attr_set[2] = {false, false};
+    if (!attr_set[epi12]) {
+        if (epi12) RMU_CUDA(cudaFuncSetAttribute(gemm_f16x3_ln_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(ln_smem_bytes(12))));
+        else RMU_CUDA(cudaFuncSetAttribute(gemm_f16x3_ln_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(ln_smem_bytes(8))));
+        attr_set[epi12] = true;
+    }
     const int m_blks = (p.M + kGemmBM - 1) / kGemmBM;
     const int clusters = std::max(1, std::min(m_blks, sms / CL));
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(static_cast<unsigned>(clusters * CL));
-    cfg.blockDim = dim3(kGemmThreads);
-    cfg.dynamicSmemBytes = kLnSmem;
+    cfg.blockDim = dim3(64 + 32 * (epi12 ? 12 : 8));
+    cfg.dynamicSmemBytes = ln_smem_bytes(epi12 ? 12 : 8);
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -134,7 +139,8 @@ int launch_gemm_ln(const SplitOperand& A, const SplitOperand& W, const GemmLnPar
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     ProfScope _ps(PROF_GEMM, st);
-    RMU_CUDA(cudaLaunchKernelEx(&cfg, gemm_f16x3_ln_kernel<kGemmEpiWarps>, A.map_hi, A.map_lo, W.map192_hi, W.map192_lo, p));
+    if (epi12) RMU_CUDA(cudaLaunchKernelEx(&cfg, gemm_f16x3_ln_kernel<12>, A.map_hi, A.map_lo, W.map192_hi, W.map192_lo, p));
+    else RMU_CUDA(cudaLaunchKernelEx(&cfg, gemm_f16x3_ln_kernel<8>, A.map_hi, A.map_lo, W.map192_hi, W.map192_lo, p));
     count_launch();
     RMU_CHECK_LAUNCH();
     return RMU_OK;

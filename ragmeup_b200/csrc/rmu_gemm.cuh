@@ -650,29 +650,39 @@ constexpr int kLnBN = 192;
 constexpr int kLnMaxCL = 4;                       // hidden <= 768
 constexpr int kLnStages = 2;
 constexpr int kLnStageBytes = 2 * kGemmPlaneBytes + 2 * kLnBN * 128;
-constexpr size_t kLnStatsBytes = 2ull * (2 * kLnMaxCL) * kGemmBM * sizeof(float2);
+// 12 epilogue warps only with clusters of 2 (hidden 384): 6 column slices; 8 warps: up to 2 * kLnMaxCL = 8 slices
+__host__ __device__ constexpr int ln_max_parts(int epi_warps) { return epi_warps == 12 ? 6 : 2 * kLnMaxCL; }
+__host__ __device__ constexpr size_t ln_stats_bytes(int epi_warps) { return 2ull * ln_max_parts(epi_warps) * kGemmBM * sizeof(float2); }
+__host__ __device__ constexpr size_t ln_staging_bytes(int epi_warps) { return static_cast<size_t>(epi_warps) * 32 * kGemmStageRow * sizeof(float); }
 constexpr size_t kLnVecBytes = 3 * kLnBN * sizeof(float);      // this CTA's bias | gamma | beta columns
-constexpr size_t kLnSmem = static_cast<size_t>(kLnStages) * kLnStageBytes + kGemmStagingBytes + kLnStatsBytes + kLnVecBytes + 256 + 1024;
+__host__ __device__ constexpr size_t ln_smem_bytes(int epi_warps) {
+    return static_cast<size_t>(kLnStages) * kLnStageBytes + ln_staging_bytes(epi_warps) + ln_stats_bytes(epi_warps) + kLnVecBytes + 256 + 1024;
+}
+static_assert(ln_smem_bytes(8) <= 232448 && ln_smem_bytes(12) <= 232448, "shared memory budget");
 
-template <int EPI_WARPS>      // = kGemmEpiWarps (two warps per TMEM lane quadrant, 96 columns each)
+template <int EPI_WARPS>      // 8 (two warps per TMEM lane quadrant, 96 columns each) or 12 (three, 64 columns each; clusters of 2)
 __global__ void __launch_bounds__(64 + 32 * EPI_WARPS, 1)
 gemm_f16x3_ln_kernel(const __grid_constant__ CUtensorMap tAh, const __grid_constant__ CUtensorMap tAl,
                      const __grid_constant__ CUtensorMap tWh, const __grid_constant__ CUtensorMap tWl,
                      const GemmLnParams p) {
-    static_assert(EPI_WARPS == kGemmEpiWarps, "statistics exchange is laid out for two 96-column parts per CTA");
+    static_assert(EPI_WARPS == 8 || EPI_WARPS == 12, "two or three epilogue warps per TMEM lane quadrant");
+    constexpr int kWQ = EPI_WARPS / 4;            // warps per lane quadrant = column slices (parts) per CTA
+    constexpr int kChunks = 6 / kWQ;              // 32-column chunks per warp
+    constexpr size_t kStagingBytes = ln_staging_bytes(EPI_WARPS);
+    constexpr int kMaxParts = ln_max_parts(EPI_WARPS);
     constexpr uint32_t IDESC = umma_idesc(0 /*f16*/, kGemmBM, kLnBN);
     constexpr int kWPlane = kLnBN * 128;
-    constexpr int kPartCols = kLnBN / 2;          // columns per epilogue warp: 3 chunks of 32
+    constexpr int kPartCols = kLnBN / kWQ;        // columns per epilogue warp
     extern __shared__ uint8_t gemm_smem_raw[];
     // 1024-byte alignment by OFFSET into the shared array: a pointer round-trip through an integer would lose the
     // shared address space and turn every staging access into a generic LD/ST
     uint8_t* smem = gemm_smem_raw + ((1024u - (smem_u32(gemm_smem_raw) & 1023u)) & 1023u);
     float* staging = reinterpret_cast<float*>(smem + kLnStages * kLnStageBytes);
-    float2* stats = reinterpret_cast<float2*>(smem + kLnStages * kLnStageBytes + kGemmStagingBytes);   // [2][2*CLmax][128]
+    float2* stats = reinterpret_cast<float2*>(smem + kLnStages * kLnStageBytes + kStagingBytes);   // [2][2*CLmax][128]
     // bias | gamma | beta of this CTA's 192 columns: the cluster-scope acquire of every tile invalidates L1, so
     // re-reading them from global memory would miss each time
-    float* svec = reinterpret_cast<float*>(smem + kLnStages * kLnStageBytes + kGemmStagingBytes + kLnStatsBytes);
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + kLnStages * kLnStageBytes + kGemmStagingBytes + kLnStatsBytes + kLnVecBytes);
+    float* svec = reinterpret_cast<float*>(smem + kLnStages * kLnStageBytes + kStagingBytes + ln_stats_bytes(EPI_WARPS));
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + kLnStages * kLnStageBytes + kStagingBytes + ln_stats_bytes(EPI_WARPS) + kLnVecBytes);
     uint64_t* empty = full + kLnStages;
     uint64_t* acc_full = empty + kLnStages;
     uint64_t* acc_empty = acc_full + 2;
@@ -687,7 +697,7 @@ gemm_f16x3_ln_kernel(const __grid_constant__ CUtensorMap tAh, const __grid_const
         for (int i = 0; i < kLnStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&acc_full[i], 1);
-            mbar_init(&acc_empty[i], 32 * kGemmEpiWarps);
+            mbar_init(&acc_empty[i], 32 * EPI_WARPS);
             mbar_init(&stat_full[i], 1);                        // armed per tile with the bytes of all 2*CL column slices
         }
         fence_mbar_init();
@@ -766,15 +776,15 @@ gemm_f16x3_ln_kernel(const __grid_constant__ CUtensorMap tAh, const __grid_const
         const int ew = warp - 2;
         const int quad = warp & 3;
         const int chalf = ew >> 2;
-        const int part = static_cast<int>(rank) * 2 + chalf;
-        const int nparts = 2 * static_cast<int>(CL);
+        const int part = static_cast<int>(rank) * kWQ + chalf;
+        const int nparts = kWQ * static_cast<int>(CL);
         float* stg = staging + ew * (32 * kGemmStageRow);
         const int rsub = static_cast<int>(lane) >> 4, cp = (static_cast<int>(lane) & 15) * 2;
         const int trow = quad * 32 + static_cast<int>(lane);           // this thread's row of the tile
         const float inv_n = 1.0f / static_cast<float>(p.N);
         // residual rows of chunk (chalf*3 + cc), coalesced: lane = column pair, 16 row pairs
         auto load_res = [&](int row_base_, int cc_, __half2 (&h)[16], __half2 (&l)[16]) {
-            const int col0_ = nb * kLnBN + (chalf * 3 + cc_) * 32;
+            const int col0_ = nb * kLnBN + (chalf * kChunks + cc_) * 32;
 #pragma unroll
             for (int q = 0; q < 16; ++q) {
                 const int grow = row_base_ + 2 * q + rsub;
@@ -802,8 +812,8 @@ gemm_f16x3_ln_kernel(const __grid_constant__ CUtensorMap tAh, const __grid_const
             //      (per-chunk mean / M2, chunks merged with Chan's formula).
             float m_loc = 0.f, m2 = 0.f;
 #pragma unroll
-            for (int cc = 0; cc < 3; ++cc) {
-                const int c = chalf * 3 + cc;
+            for (int cc = 0; cc < kChunks; ++cc) {
+                const int c = chalf * kChunks + cc;
                 const float2 bia2 = *reinterpret_cast<const float2*>(svec + c * 32 + cp);
 #pragma unroll
                 for (int rr = 0; rr < 32; rr += 2) {
@@ -813,7 +823,7 @@ gemm_f16x3_ln_kernel(const __grid_constant__ CUtensorMap tAh, const __grid_const
                     stg[rl * kGemmStageRow + cp] = bia2.x + (fh.x + fl.x);
                     stg[rl * kGemmStageRow + cp + 1] = bia2.y + (fh.y + fl.y);
                 }
-                if (cc < 2) load_res(row_base, cc + 1, rsh, rsl);      // in flight during the rest of this chunk
+                if (cc + 1 < kChunks) load_res(row_base, cc + 1, rsh, rsl);      // in flight during the rest of this chunk
                 __syncwarp();
                 if (cc == 0) {
                     mbar_wait(&acc_full[buf], use & 1);
@@ -847,31 +857,31 @@ gemm_f16x3_ln_kernel(const __grid_constant__ CUtensorMap tAh, const __grid_const
             if (mb + n_clusters < m_blks) load_res((mb + n_clusters) * kGemmBM + quad * 32, 0, rsh, rsl);
             // ---- exchange (mean, M2) of (row, part) with every CTA of the cluster
             const int sbuf = i & 1;
-            float2* my = stats + (static_cast<size_t>(sbuf) * (2 * kLnMaxCL) + part) * kGemmBM + trow;
+            float2* my = stats + (static_cast<size_t>(sbuf) * kMaxParts + part) * kGemmBM + trow;
             if (ew == 0 && lane == 0) mbar_arrive_expect_tx(&stat_full[sbuf], static_cast<uint32_t>(kGemmBM * nparts * sizeof(float2)));
             for (uint32_t c = 0; c < CL; ++c) st_async_cluster_f2(my, &stat_full[sbuf], c, make_float2(m_loc, m2));
             mbar_wait(&stat_full[sbuf], use & 1);
             float mean = 0.f;
-            for (int q = 0; q < nparts; ++q) mean += stats[(static_cast<size_t>(sbuf) * (2 * kLnMaxCL) + q) * kGemmBM + trow].x;
+            for (int q = 0; q < nparts; ++q) mean += stats[(static_cast<size_t>(sbuf) * kMaxParts + q) * kGemmBM + trow].x;
             mean /= static_cast<float>(nparts);
             float M2 = 0.f;
             for (int q = 0; q < nparts; ++q) {
-                const float2 s2 = stats[(static_cast<size_t>(sbuf) * (2 * kLnMaxCL) + q) * kGemmBM + trow];
+                const float2 s2 = stats[(static_cast<size_t>(sbuf) * kMaxParts + q) * kGemmBM + trow];
                 const float d = s2.x - mean;
                 M2 += s2.y + static_cast<float>(kPartCols) * d * d;
             }
             const float rstd = 1.0f / sqrtf(M2 * inv_n + p.eps);
             // ---- pass C: normalise, gamma / beta in the column-pair layout, split, coalesced plane stores
 #pragma unroll 1
-            for (int cc = 0; cc < 3; ++cc) {
-                const int c = chalf * 3 + cc;
+            for (int cc = 0; cc < kChunks; ++cc) {
+                const int c = chalf * kChunks + cc;
                 const int col0 = nb * kLnBN + c * 32;
                 const float2 g2 = *reinterpret_cast<const float2*>(svec + kLnBN + c * 32 + cp);
                 const float2 b2 = *reinterpret_cast<const float2*>(svec + 2 * kLnBN + c * 32 + cp);
                 uint32_t r[32];
                 tmem_ld32(tmem_addr(tmem_base, quad * 32, buf * kLnBN + c * 32), r);
                 tmem_ld_wait();
-                if (cc == 2) {                       // last TMEM read of this warp for the tile
+                if (cc == kChunks - 1) {                       // last TMEM read of this warp for the tile
                     tc_fence_before();
                     mbar_arrive(&acc_empty[buf]);
                 }

@@ -17,7 +17,7 @@ for r in rows[1:]:
     name = r[ki]
     name = name.split("(")[0].replace("void ", "").replace("rmu::", "")
     if not name.startswith(("scan_", "finalize", "exact", "select_tau", "compact", "merge", "gemm_", "attention", "ln_kernel",
-                            "embed_ln", "pool_", "cls_head", "row_stats", "gather_rows", "mmr", "split_planes", "join_planes")):
+                            "embed_ln", "pool_", "cls_head", "row_stats", "gather_rows", "mmr", "split_planes", "join_planes", "bm25_")):
         name = "torch/other: " + name[:40]
     tot[name] += v * scale; cnt[name] += 1
 ours = {k: v for k, v in tot.items() if not k.startswith("torch/other")}
