@@ -453,8 +453,8 @@ __device__ __forceinline__ float fast_exp2(float x) {   // ex2.approx: 2 ulp, ex
 // to 3 CTAs / 64 registers spills in the key loop and measured 541 us instead of 352 us per layer call).
 // Grid = (heads, sequences, row blocks): the heads of one sequence run together, so the 64-byte (d_h = 32)
 // K / V row segments of neighbouring heads are fetched from DRAM as whole lines.
-template <int DH, int MINB>
-__global__ void __launch_bounds__(kAttWarps * 32, MINB) attention_planes_kernel(const __half* __restrict__ ph, const __half* __restrict__ pl,
+template <int DH, int MINB, int NW = kAttWarps>      // NW warps = 16 * NW query rows per CTA
+__global__ void __launch_bounds__(NW * 32, MINB) attention_planes_kernel(const __half* __restrict__ ph, const __half* __restrict__ pl,
                                                                           const int* __restrict__ cu, int H, int ksb,
                                                                           __half* __restrict__ ctx_hi, __half* __restrict__ ctx_lo) {
     constexpr int KSTR = DH + 8;
@@ -468,7 +468,7 @@ __global__ void __launch_bounds__(kAttWarps * 32, MINB) attention_planes_kernel(
 
     const int b = blockIdx.y, h = blockIdx.x;
     const int t0 = cu[b], S = cu[b + 1] - t0;
-    const int rbase = blockIdx.z * (kAttWarps * 16);
+    const int rbase = blockIdx.z * (NW * 16);
     if (rbase >= S) return;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
     const size_t ld = static_cast<size_t>(3) * H;
@@ -860,20 +860,24 @@ static int run_encoder(rmu_encoder* e, const int32_t* ids, const int32_t* type_i
         {
             ProfScope _ps(PROF_ATTN, st);
             if (attn_mode == 0) {
+                // RMU_ATTN_WARPS = 5: 80-row CTAs, four per SM (same warps/SM, K/V staged twice per 147-token sequence)
+                static const int nw_env = [] { const char* e = getenv("RMU_ATTN_WARPS"); return e ? atoi(e) : kAttWarps; }();
+                const int nw = (nw_env == 5 && DH == 32) ? 5 : kAttWarps;
                 dim3 pg(static_cast<unsigned>(c.heads), static_cast<unsigned>(B),
-                        static_cast<unsigned>((max_seqlen + kAttWarps * 16 - 1) / (kAttWarps * 16)));
+                        static_cast<unsigned>((max_seqlen + nw * 16 - 1) / (nw * 16)));
                 // keys resident per CTA: the whole (longest) sequence when it fits, else super-blocks of kKeySB
                 const int ksb = std::min(kKeySB, (max_seqlen + 31) / 32 * 32);
                 const size_t smem_max = 4 * sizeof(__half) * static_cast<size_t>(kKeySB) * (DH + 8);
                 const size_t smem = 4 * sizeof(__half) * static_cast<size_t>(ksb) * (DH + 8);
-                auto kern = DH == 32 ? attention_planes_kernel<32, 2> : attention_planes_kernel<64, 1>;   // d_h = 64 needs > 96 registers
-                static bool attr_set[2] = {false, false};
-                const int ki = DH == 32 ? 0 : 1;
+                auto kern = DH == 32 ? (nw == 5 ? attention_planes_kernel<32, 4, 5> : attention_planes_kernel<32, 2>)
+                                     : attention_planes_kernel<64, 1>;   // d_h = 64 needs > 96 registers
+                static bool attr_set[3] = {false, false, false};
+                const int ki = DH == 32 ? (nw == 5 ? 2 : 0) : 1;
                 if (!attr_set[ki]) {
                     RMU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_max)));
                     attr_set[ki] = true;
                 }
-                kern<<<pg, kAttWarps * 32, smem, st>>>(e->QKVP.hi, e->QKVP.lo, cu, H, ksb, e->CTX.hi, e->CTX.lo);
+                kern<<<pg, nw * 32, smem, st>>>(e->QKVP.hi, e->QKVP.lo, cu, H, ksb, e->CTX.hi, e->CTX.lo);
             } else if (attn_mode == 2) {
                 if (DH == 32) attention_kernel<32><<<ag, 128, 0, st>>>(e->QKV, cu, H, scale, e->CTX.hi, e->CTX.lo);
                 else attention_kernel<64><<<ag, 128, 0, st>>>(e->QKV, cu, H, scale, e->CTX.hi, e->CTX.lo);
