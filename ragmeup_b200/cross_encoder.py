@@ -15,8 +15,10 @@ import numpy as np
 
 from .embeddings import _check_device
 from .encoder import MAX_TOKENS_PER_CALL, BertEncoder
-from .tokenizer import RaggedTokenizer, load_tokenizer
+from .tokenizer import RaggedTokenizer, load_tokenizer, pipelined
 from .weights import resolve_model
+
+PIPE_PAIRS = 512      # pairs per pipelined chunk of a bulk score() call (one 100-pair rerank is a single chunk)
 
 
 class BaseCrossEncoder:
@@ -52,10 +54,11 @@ class HuggingFaceCrossEncoder(BaseCrossEncoder):
         if len(pairs) == 0:
             # sentence-transformers 2.6.1 raises on an empty list; keep the behaviour
             raise IndexError("score() received no text pairs")
-        a = [p[0].strip() for p in pairs]
-        b = [p[1].strip() for p in pairs]
-        ids, typ, cu = self._ragged(a, b)
-        return self._post(self.client.classify_host(ids, typ, cu))
+        # bulk calls: pairs in chunks, WordPiece of chunk i+1 overlapped with the device scoring of chunk i
+        chunks = [pairs[s:s + PIPE_PAIRS] for s in range(0, len(pairs), PIPE_PAIRS)]
+        outs = pipelined(chunks, lambda c: self._ragged([p[0].strip() for p in c], [p[1].strip() for p in c]),
+                         lambda t: self.client.classify_host(*t))
+        return self._post(outs[0] if len(outs) == 1 else np.concatenate(outs, 0))
 
     def score_tensor(self, text_pairs: Sequence[Tuple[str, str]]):
         """same scores as a CUDA fp32 tensor [n] (stays on the device)."""

@@ -20,8 +20,10 @@ import numpy as np
 
 from . import _lib
 from .encoder import MAX_TOKENS_PER_CALL, BertEncoder
-from .tokenizer import RaggedTokenizer, load_tokenizer
+from .tokenizer import RaggedTokenizer, load_tokenizer, pipelined
 from .weights import resolve_model
+
+PIPE_TEXTS = 1000     # texts per pipelined chunk of a bulk embed_documents() call
 
 
 def _check_device(model_kwargs: Optional[Dict[str, Any]]) -> Optional[int]:
@@ -78,8 +80,10 @@ class HuggingFaceEmbeddings:
         if len(texts) == 0:
             return np.zeros((0, self.config.hidden), dtype=np.float32)
         texts = [t.replace("\n", " ").strip() for t in texts]
-        ids, typ, cu = self._ragged(texts)
-        return self.client.embed_host(ids, typ, cu, self.pooling, self.normalize)
+        # bulk calls: WordPiece of chunk i+1 overlapped with the device encode of chunk i
+        chunks = [texts[s:s + PIPE_TEXTS] for s in range(0, len(texts), PIPE_TEXTS)]
+        outs = pipelined(chunks, self._ragged, lambda t: self.client.embed_host(t[0], t[1], t[2], self.pooling, self.normalize))
+        return outs[0] if len(outs) == 1 else np.concatenate(outs, 0)
 
     # -- the reference surface
     def embed_documents(self, texts: List[str]) -> List[List[float]]:

@@ -12,6 +12,7 @@ batches into the ragged ``cu_seqlens`` layout the CUDA encoder consumes
 from __future__ import annotations
 
 import os
+from concurrent.futures import ThreadPoolExecutor
 from itertools import chain
 from typing import Dict, List, Optional, Sequence, Tuple
 
@@ -135,3 +136,22 @@ def _pack(enc) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
     ids = np.fromiter(chain.from_iterable(id_lists), dtype=np.int32, count=total)
     typ = np.fromiter(chain.from_iterable(e.type_ids for e in enc), dtype=np.int32, count=total)
     return ids, typ, cu
+
+
+def pipelined(chunks: Sequence, tokenize, run) -> List:
+    """``[run(tokenize(c)) for c in chunks]`` with the tokenisation of chunk i+1 (host, HF `tokenizers` releases the
+    GIL) overlapped with the device call of chunk i (ctypes releases the GIL while it waits on the stream).  On a B200
+    the encoder consumes tokens faster than WordPiece produces them, so for bulk calls the host side is what is left
+    to hide."""
+    chunks = list(chunks)
+    if len(chunks) <= 1:
+        return [run(tokenize(c)) for c in chunks]
+    out = []
+    with ThreadPoolExecutor(max_workers=1) as ex:
+        fut = ex.submit(tokenize, chunks[0])
+        for i in range(len(chunks)):
+            tok = fut.result()
+            if i + 1 < len(chunks):
+                fut = ex.submit(tokenize, chunks[i + 1])
+            out.append(run(tok))
+    return out

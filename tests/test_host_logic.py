@@ -120,3 +120,32 @@ def test_install_shims():
     assert E is c["HuggingFaceEmbeddings"] and M is c["Milvus"] and P is c["PGVector"]
     assert X is c["HuggingFaceCrossEncoder"] and S is c["ScoredCrossEncoderReranker"]
     assert "langchain_milvus.vectorstores" in sys.modules
+
+
+def test_pipelined_overlaps_and_keeps_order():
+    import threading
+    import time
+    from ragmeup_b200.tokenizer import pipelined
+    seen = []
+
+    def tok(c):
+        seen.append(("tok", c, threading.current_thread() is threading.main_thread()))
+        time.sleep(0.04)
+        return c * 2
+
+    def run(t):
+        seen.append(("run", t))
+        time.sleep(0.04)
+        return t + 1
+
+    t0 = time.time()
+    assert pipelined([1, 2, 3, 4], tok, run) == [3, 5, 7, 9]
+    assert time.time() - t0 < 0.29                       # serial would be 0.32 s; overlapped ~0.20 s
+    assert [s[1] for s in seen if s[0] == "run"] == [2, 4, 6, 8]
+    assert not any(s[2] for s in seen if s[0] == "tok")  # tokenisation runs off the calling thread
+    assert pipelined([], tok, run) == [] and pipelined([5], tok, run) == [11]
+
+    def bad(c):
+        raise ValueError("boom")
+    with pytest.raises(ValueError):
+        pipelined([1, 2], bad, run)
