@@ -15,7 +15,7 @@ import numpy as np
 
 from .embeddings import _check_device
 from .encoder import MAX_TOKENS_PER_CALL, BertEncoder
-from .tokenizer import RaggedTokenizer, load_tokenizer, pipelined
+from .tokenizer import PairAssembler, RaggedTokenizer, load_tokenizer, pipelined
 from .weights import resolve_model
 
 PIPE_PAIRS = 512      # pairs per pipelined chunk of a bulk score() call (one 100-pair rerank is a single chunk)
@@ -41,6 +41,8 @@ class HuggingFaceCrossEncoder(BaseCrossEncoder):
         self.activation = activation
         self.tokenizer = load_tokenizer(vocab_src, cfg.vocab_size)
         self._ragged = RaggedTokenizer(self.tokenizer, self.max_length)
+        # pair batches assembled from cached per-text WordPiece ids (identical to self._ragged(a, b); tests/test_host_logic.py)
+        self._pairs = PairAssembler(self.tokenizer, self.max_length)
         self.client = BertEncoder(cfg, w, with_head=True, device=device)
 
     def _post(self, logits: np.ndarray) -> np.ndarray:
@@ -56,7 +58,7 @@ class HuggingFaceCrossEncoder(BaseCrossEncoder):
             raise IndexError("score() received no text pairs")
         # bulk calls: pairs in chunks, WordPiece of chunk i+1 overlapped with the device scoring of chunk i
         chunks = [pairs[s:s + PIPE_PAIRS] for s in range(0, len(pairs), PIPE_PAIRS)]
-        outs = pipelined(chunks, lambda c: self._ragged([p[0].strip() for p in c], [p[1].strip() for p in c]),
+        outs = pipelined(chunks, lambda c: self._pairs([p[0].strip() for p in c], [p[1].strip() for p in c]),
                          lambda t: self.client.classify_host(*t))
         return self._post(outs[0] if len(outs) == 1 else np.concatenate(outs, 0))
 
@@ -68,7 +70,7 @@ class HuggingFaceCrossEncoder(BaseCrossEncoder):
             raise IndexError("score_tensor() received no text pairs")
         a = [p[0].strip() for p in pairs]
         b = [p[1].strip() for p in pairs]
-        ids, typ, cu = self._ragged(a, b)
+        ids, typ, cu = self._pairs(a, b)
         outs = []
         for s, e in BertEncoder._chunks(cu, MAX_TOKENS_PER_CALL):
             t0, t1 = int(cu[s]), int(cu[e])

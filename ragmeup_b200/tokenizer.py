@@ -12,6 +12,7 @@ batches into the ragged ``cu_seqlens`` layout the CUDA encoder consumes
 from __future__ import annotations
 
 import os
+import threading
 from concurrent.futures import ThreadPoolExecutor
 from itertools import chain
 from typing import Dict, List, Optional, Sequence, Tuple
@@ -155,3 +156,74 @@ def pipelined(chunks: Sequence, tokenize, run) -> List:
                 fut = ex.submit(tokenize, chunks[i + 1])
             out.append(run(tok))
     return out
+
+
+class PairAssembler:
+    """(text_a, text_b) pairs -> the ragged ``[CLS] a [SEP] b [SEP]`` batch of ``RaggedTokenizer(a, b)``, built from
+    PER-TEXT WordPiece ids that are cached.  A reranker scores the same documents against many queries (and the same
+    query against many documents): with the cache only unseen texts reach the tokeniser, and on a B200 the tokeniser,
+    not the encoder, bounds a text-level rerank (6400 pairs: 214 ms of WordPiece vs 90 ms of GPU).
+
+    Equality with pair tokenisation rests on two facts checked in tests/test_host_logic.py: BERT normalisation and
+    pre-tokenisation act on each segment separately, and `truncation="longest_first"` in HF `tokenizers` is the closed
+    form below (shorter side n1, longer n2: n2 = max(n1, B - n1); if still too long n1 = B // 2, n2 = n1 + B % 2), with
+    B = max_length minus the three special tokens."""
+
+    def __init__(self, tok: Tokenizer, max_length: int, max_entries: int = 1 << 18):
+        self.max_length = int(max_length)
+        self._tok = Tokenizer.from_str(tok.to_str())
+        self._tok.no_truncation()
+        self._tok.no_padding()
+        self._cls = tok.token_to_id("[CLS]")
+        self._sep = tok.token_to_id("[SEP]")
+        if self._cls is None or self._sep is None:
+            raise ValueError("PairAssembler needs a BERT vocabulary with [CLS] and [SEP]")
+        self._cache: Dict[str, np.ndarray] = {}
+        self._max_entries = int(max_entries)
+        self._lock = threading.Lock()
+
+    def _ids(self, texts: Sequence[str]) -> List[np.ndarray]:
+        got: Dict[str, np.ndarray] = {}
+        with self._lock:
+            for t in dict.fromkeys(texts):
+                v = self._cache.get(t)
+                if v is not None:
+                    got[t] = v
+        missing = [t for t in dict.fromkeys(texts) if t not in got]
+        if missing:
+            enc = self._tok.encode_batch(missing, add_special_tokens=False)      # outside the lock: releases the GIL
+            fresh = {t: np.asarray(e.ids, dtype=np.int32) for t, e in zip(missing, enc)}
+            got.update(fresh)
+            with self._lock:
+                self._cache.update(fresh)
+                while len(self._cache) > self._max_entries:                      # oldest first
+                    self._cache.pop(next(iter(self._cache)))
+        return [got[t] for t in texts]
+
+    def __call__(self, texts_a: Sequence[str], texts_b: Sequence[str]) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+        ia, ib = self._ids(list(texts_a)), self._ids(list(texts_b))
+        la = np.fromiter(map(len, ia), dtype=np.int64, count=len(ia))
+        lb = np.fromiter(map(len, ib), dtype=np.int64, count=len(ib))
+        budget = self.max_length - 3
+        swap = la > lb
+        n1, n2 = np.where(swap, lb, la), np.where(swap, la, lb)
+        over = la + lb > budget
+        n2t = np.maximum(n1, budget - n1)
+        both = n1 + n2t > budget
+        n1t = np.where(both, budget // 2, n1)
+        n2t = np.where(both, budget // 2 + budget % 2, n2t)
+        na = np.where(over, np.where(swap, n2t, n1t), la)
+        nb = np.where(over, np.where(swap, n1t, n2t), lb)
+        cu = np.zeros(len(ia) + 1, dtype=np.int32)
+        np.cumsum(na + nb + 3, out=cu[1:])
+        cls = np.asarray([self._cls], dtype=np.int32)
+        sep = np.asarray([self._sep], dtype=np.int32)
+        pieces = []
+        for a, b, x, y in zip(ia, ib, na, nb):
+            pieces += (cls, a[:x], sep, b[:y], sep)
+        ids = np.concatenate(pieces) if pieces else np.zeros(0, dtype=np.int32)
+        typ = np.zeros(int(cu[-1]), dtype=np.int32)
+        starts = cu[:-1] + na.astype(np.int32) + 2                 # first token of segment b
+        for s0, e0 in zip(starts, cu[1:]):
+            typ[s0:e0] = 1
+        return ids, typ, cu

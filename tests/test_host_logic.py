@@ -149,3 +149,30 @@ def test_pipelined_overlaps_and_keeps_order():
         raise ValueError("boom")
     with pytest.raises(ValueError):
         pipelined([1, 2], bad, run)
+
+
+def test_pair_assembler_equals_pair_tokenisation():
+    """[CLS] a [SEP] b [SEP] built from cached per-text ids == HF pair tokenisation with truncation='longest_first',
+    across truncation regimes (both sides cut, one side cut, none), empty texts and cache eviction."""
+    from ragmeup_b200.tokenizer import PairAssembler, RaggedTokenizer, load_tokenizer, synthetic_sentences, synthetic_vocab
+    tok = load_tokenizer(None, 30522)
+    vocab = synthetic_vocab(30522)
+    rng = np.random.default_rng(0)
+    a = synthetic_sentences(vocab, 200, 0, 40, seed=1) + ["", "x", "  ", "Ünïcode çase Test", "a\tb\nc"]
+    b = synthetic_sentences(vocab, 200, 0, 60, seed=2) + ["y", "", "z z z", "MiXed CASE words", " nbsp"]
+    for max_length in (12, 20, 64, 512):
+        rt, pa = RaggedTokenizer(tok, max_length), PairAssembler(tok, max_length, max_entries=64)
+        for _ in range(3):                                   # repeated calls: cache hits and evictions
+            ia = [a[int(i)].strip() for i in rng.integers(0, len(a), 300)]
+            ib = [b[int(i)].strip() for i in rng.integers(0, len(b), 300)]
+            want, got = rt(ia, ib), pa(ia, ib)
+            assert all(np.array_equal(x, y) for x, y in zip(want, got)), max_length
+        assert len(pa._cache) <= 64
+    # every (len_a, len_b) combination around the budget
+    words = [w for w in vocab if w.isalpha() and len(w) > 2][:40]
+    rt, pa = RaggedTokenizer(tok, 16), PairAssembler(tok, 16)
+    ia = [" ".join(words[:n]) for n in range(0, 20) for _ in range(20)]
+    ib = [" ".join(words[20:20 + m]) for _ in range(20) for m in range(0, 20)]
+    assert all(np.array_equal(x, y) for x, y in zip(rt(ia, ib), pa(ia, ib)))
+    e = pa([], [])
+    assert e[0].size == 0 and e[2].tolist() == [0]
