@@ -4,7 +4,8 @@ Follows ``server/provenance.py:100-108`` (``compute_rerank_provenance``) and ``:
 (``DocumentSimilarityAttribution.compute_similarity``): ``SentenceTransformer.encode`` (restated in
 ``bert_ref.st_encode``), sklearn ``cosine_similarity`` (rows L2-normalised, zero rows left at zero, then a dot
 product, all in the input dtype float32), the average with the query similarity, and the division by the sum.
-PARITY STATUS: unpinned by the reference repository (no tests there); sklearn / sentence-transformers are restated.
+PARITY STATUS: unpinned by the reference repository (no tests there); sentence-transformers is restated, the sklearn
+cosine restatement is checked against the real scikit-learn in tests/test_hybrid_cpu.py.
 """
 from __future__ import annotations
 

@@ -218,3 +218,19 @@ def test_cpp_index_builder_property():
         _check_same_index(texts)
 
     prop()
+
+
+def test_cosine_restatement_pinned_against_sklearn():
+    """oracle/provenance_ref.sk_cosine_similarity vs the real sklearn.metrics.pairwise.cosine_similarity (installed in
+    this image; the reference imports it at server/provenance.py:6) — float32 inputs, zero rows included."""
+    sk = pytest.importorskip("sklearn.metrics.pairwise")
+    from oracle import provenance_ref as P
+    rng = np.random.default_rng(3)
+    X = rng.standard_normal((17, 384)).astype(np.float32)
+    Y = rng.standard_normal((5, 384)).astype(np.float32)
+    X[4] = 0.0
+    Y[2] = 0.0
+    want = sk.cosine_similarity(X, Y)
+    got = P.sk_cosine_similarity(X, Y)
+    assert got.dtype == want.dtype == np.float32
+    assert np.abs(got - want).max() < 2e-7 and np.all(got[4] == 0) and np.all(got[:, 2] == 0)
