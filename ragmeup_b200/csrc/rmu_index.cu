@@ -1098,19 +1098,25 @@ void rmu_index_destroy(rmu_index* idx) {
     delete idx;
 }
 
-int rmu_index_reserve(rmu_index* idx, int64_t rows) {
-    if (!idx || rows < 0) { set_error("rmu_index_reserve: bad argument"); return RMU_ERR_ARG; }
-    std::lock_guard<std::mutex> g(idx->mu);
+}  // extern "C"
+
+// grow the corpus allocation to `rows` rows; idx->mu must be held
+static int reserve_locked(rmu_index* idx, int64_t rows) {
     if (rows <= idx->cap) return RMU_OK;
     RMU_CUDA(cudaDeviceSynchronize());
     float* nx = nullptr; float* ns = nullptr; float* nb = nullptr;
-    RMU_CUDA(cudaMalloc(&nx, static_cast<size_t>(rows) * idx->dim * sizeof(float)));
-    RMU_CUDA(cudaMalloc(&ns, static_cast<size_t>(rows) * sizeof(float)));
-    RMU_CUDA(cudaMalloc(&nb, static_cast<size_t>(rows) * sizeof(float)));
-    if (idx->n > 0) {
-        RMU_CUDA(cudaMemcpy(nx, idx->x, static_cast<size_t>(idx->n) * idx->dim * sizeof(float), cudaMemcpyDeviceToDevice));
-        RMU_CUDA(cudaMemcpy(ns, idx->rscale, static_cast<size_t>(idx->n) * sizeof(float), cudaMemcpyDeviceToDevice));
-        RMU_CUDA(cudaMemcpy(nb, idx->rbias, static_cast<size_t>(idx->n) * sizeof(float), cudaMemcpyDeviceToDevice));
+    cudaError_t e = cudaMalloc(&nx, static_cast<size_t>(rows) * idx->dim * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&ns, static_cast<size_t>(rows) * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&nb, static_cast<size_t>(rows) * sizeof(float));
+    if (e == cudaSuccess && idx->n > 0) {
+        e = cudaMemcpy(nx, idx->x, static_cast<size_t>(idx->n) * idx->dim * sizeof(float), cudaMemcpyDeviceToDevice);
+        if (e == cudaSuccess) e = cudaMemcpy(ns, idx->rscale, static_cast<size_t>(idx->n) * sizeof(float), cudaMemcpyDeviceToDevice);
+        if (e == cudaSuccess) e = cudaMemcpy(nb, idx->rbias, static_cast<size_t>(idx->n) * sizeof(float), cudaMemcpyDeviceToDevice);
+    }
+    if (e != cudaSuccess) {
+        cudaFree(nx); cudaFree(ns); cudaFree(nb);            // the index keeps its old storage
+        set_error(std::string("rmu_index_reserve: ") + cudaGetErrorString(e));
+        return RMU_ERR_CUDA;
     }
     cudaFree(idx->x); cudaFree(idx->rscale); cudaFree(idx->rbias);
     idx->x = nx; idx->rscale = ns; idx->rbias = nb;
@@ -1119,16 +1125,24 @@ int rmu_index_reserve(rmu_index* idx, int64_t rows) {
     return RMU_OK;
 }
 
+extern "C" {
+
+int rmu_index_reserve(rmu_index* idx, int64_t rows) {
+    if (!idx || rows < 0) { set_error("rmu_index_reserve: bad argument"); return RMU_ERR_ARG; }
+    std::lock_guard<std::mutex> g(idx->mu);
+    return reserve_locked(idx, rows);
+}
+
 int rmu_index_add(rmu_index* idx, const float* vecs, int64_t n, int src_is_host, void* stream) {
     if (!idx || (n > 0 && !vecs) || n < 0) { set_error("rmu_index_add: bad argument"); return RMU_ERR_ARG; }
     if (n == 0) return RMU_OK;
+    std::lock_guard<std::mutex> g(idx->mu);      // size check, growth and append are one critical section
     if (idx->n + n > static_cast<int64_t>(0xFFFFFFF0u)) { set_error("rmu_index_add: more than 2^32 rows per shard"); return RMU_ERR_UNSUPPORTED; }
     if (idx->n + n > idx->cap) {
         int64_t want = std::max<int64_t>(idx->n + n, idx->cap + idx->cap / 2);
-        int rc = rmu_index_reserve(idx, std::max<int64_t>(want, 1024));
+        int rc = reserve_locked(idx, std::max<int64_t>(want, 1024));
         if (rc != RMU_OK) return rc;
     }
-    std::lock_guard<std::mutex> g(idx->mu);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     RMU_CUDA(cudaMemcpyAsync(idx->x + idx->n * idx->dim, vecs, static_cast<size_t>(n) * idx->dim * sizeof(float),
                              src_is_host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, st));
