@@ -56,3 +56,67 @@ def test_mmr_is_a_duplicate_free_prefix_selection(n, k, lam, seed):
     if sel:
         assert sel[0] == int(np.argmax(flat_ref.cosine_similarity(q[None], E)[0]))
         assert flat_ref.mmr(q, E, lambda_mult=lam, k=len(sel) + 1)[: len(sel)] == sel      # greedy: prefixes nest
+
+
+def _tf32(a: np.ndarray, mode: str) -> np.ndarray:
+    """fp32 -> TF32 (10 explicit mantissa bits) by truncation or round-to-nearest-even, as float32."""
+    u = np.ascontiguousarray(a, dtype=np.float32).view(np.uint32).copy()
+    if mode == "rn":
+        u = u + np.uint32(0x0FFF) + ((u >> np.uint32(13)) & np.uint32(1))
+    return (u & np.uint32(0xFFFFE000)).view(np.float32)
+
+
+@settings(max_examples=40, deadline=None)
+@given(d=st.sampled_from([4, 96, 384, 768]), scale_q=st.sampled_from([1e-3, 1.0, 37.0]), scale_x=st.sampled_from([1e-2, 1.0, 250.0]),
+       shape=st.sampled_from(["normal", "same_sign", "heavy"]), mode=st.sampled_from(["trunc", "rn"]), seed=st.integers(0, 10_000))
+def test_tf32_coarse_key_error_is_inside_the_certificate_margin(d, scale_q, scale_x, shape, mode, seed):
+    """The certificate of the tensor scan assumes |<tf32(q), tf32(x)> - <q, x>| <= 2.2e-3 * |q| * |x|
+    whichever way the tensor core reduces fp32 operands to TF32 (truncation or rounding of both operands:
+    (1 + 2^-10)^2 - 1 < 2^-9 per product, Cauchy-Schwarz over the sum).  Checked here on adversarial shapes,
+    including all-same-sign vectors where the errors cannot cancel."""
+    rng = np.random.default_rng(seed)
+    def draw(n):
+        if shape == "normal":
+            v = rng.standard_normal((n, d))
+        elif shape == "same_sign":
+            v = np.abs(rng.standard_normal((n, d))) + 0.999          # mantissas just below a power of two lose the most
+        else:
+            v = rng.standard_cauchy((n, d))
+        return v.astype(np.float32)
+    q = draw(4) * np.float32(scale_q)
+    x = draw(64) * np.float32(scale_x)
+    exact = q.astype(np.float64) @ x.astype(np.float64).T
+    coarse = _tf32(q, mode).astype(np.float64) @ _tf32(x, mode).astype(np.float64).T
+    bound = 2.2e-3 * np.linalg.norm(q.astype(np.float64), axis=1)[:, None] * np.linalg.norm(x.astype(np.float64), axis=1)[None, :]
+    # fp32 accumulation of d products adds at most ~d * 2^-24 relative to sum |q_i x_i| <= |q||x|
+    slack = d * 2.0 ** -24 * np.linalg.norm(q.astype(np.float64), axis=1)[:, None] * np.linalg.norm(x.astype(np.float64), axis=1)[None, :]
+    assert np.all(np.abs(coarse - exact) <= bound - slack)
+
+
+@settings(max_examples=30, deadline=None)
+@given(k=st.sampled_from([64, 384, 1536]), scale=st.sampled_from([1e-2, 1.0, 30.0]), seed=st.integers(0, 10_000))
+def test_fp16_split_three_term_product_is_fp32_grade(k, scale, seed):
+    """The encoder GEMMs carry fp32 operands as fp16 planes v = hi + lo and sum hi*hi + lo*hi + hi*lo.
+    hi + lo reproduces v to max(2^-21 |v|, 2^-25) (the lo plane of a value below ~0.06 is an fp16 subnormal, spacing
+    2^-24: an ABSOLUTE 3e-8, harmless for a 1e-3 bar), and the dropped lo*lo term is 2^-22 of the product, so the 3-term
+    sum is within a few 2^-21 |a||w| (+ that absolute floor) of the exact dot product — the fp32 noise floor — whereas a
+    single fp16 term is ~2^-11."""
+    rng = np.random.default_rng(seed)
+    a = (rng.standard_normal((8, k)) * scale).astype(np.float32)
+    w = (rng.standard_normal((16, k)) * 0.05).astype(np.float32)
+
+    def split(v):
+        hi = v.astype(np.float16)
+        lo = (v - hi.astype(np.float32)).astype(np.float16)
+        return hi.astype(np.float64), lo.astype(np.float64)
+
+    ah, al = split(a)
+    wh, wl = split(w)
+    assert np.all(np.abs((ah + al) - a) <= np.maximum(2.0 ** -21 * np.abs(a), 2.0 ** -25))
+    exact = a.astype(np.float64) @ w.astype(np.float64).T
+    three = ah @ wh.T + al @ wh.T + ah @ wl.T
+    one = ah @ wh.T
+    norm = np.linalg.norm(a.astype(np.float64), axis=1)[:, None] * np.linalg.norm(w.astype(np.float64), axis=1)[None, :]
+    floor = 2.0 ** -25 * (np.abs(w).sum(axis=1)[None, :] + np.abs(a).sum(axis=1)[:, None])
+    assert np.all(np.abs(three - exact) <= 4 * 2.0 ** -21 * norm + floor)
+    assert np.abs(one - exact).max() > 20 * np.abs(three - exact).max()
