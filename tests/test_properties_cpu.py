@@ -19,9 +19,20 @@ def test_shard_merge_equals_full_search(n, d, nq, k, R, metric, seed):
     bounds = [n * r // R for r in range(R + 1)]
     parts = [flat_ref.flat_search(q, x[bounds[r]:bounds[r + 1]], k, metric, id_offset=bounds[r]) for r in range(R)]
     ms, mi = flat_ref.shard_merge(np.stack([p[0] for p in parts]), np.stack([p[1] for p in parts]), metric)
-    assert (mi == fi).all()
     valid = fi >= 0
+    assert (mi >= 0).tolist() == valid.tolist()
     assert np.allclose(ms[valid], fs[valid], atol=1e-6)
+    # ids are identical wherever the scores decide; the planted duplicate has mathematically EQUAL scores in two shards,
+    # and numpy's BLAS may round the same dot product differently for a 1-row and a 2-row shard (found by hypothesis:
+    # n=4, R=3), so inside a tie (|gap| <= 1e-6) only the set of rows is compared
+    for qi in range(nq):
+        f_ids, m_ids, f_s = fi[qi][valid[qi]], mi[qi][valid[qi]], fs[qi][valid[qi]].astype(np.float64)
+        lo = 0
+        for j in range(1, len(f_ids)):
+            if abs(f_s[j] - f_s[j - 1]) > 1e-6:          # a tie group that ends inside the list: same rows in it
+                assert sorted(f_ids[lo:j].tolist()) == sorted(m_ids[lo:j].tolist())
+                lo = j
+        # (the last group may be cut by k inside a tie: its members are only known to carry the same scores)
 
 
 @settings(max_examples=25, deadline=None)
@@ -120,3 +131,42 @@ def test_fp16_split_three_term_product_is_fp32_grade(k, scale, seed):
     floor = 2.0 ** -25 * (np.abs(w).sum(axis=1)[None, :] + np.abs(a).sum(axis=1)[:, None])
     assert np.all(np.abs(three - exact) <= 4 * 2.0 ** -21 * norm + floor)
     assert np.abs(one - exact).max() > 20 * np.abs(three - exact).max()
+
+
+@settings(max_examples=40, deadline=None)
+@given(h=st.sampled_from([384, 768]), mean=st.sampled_from([0.0, 3.0, -250.0]), std=st.sampled_from([1e-3, 1.0, 40.0]),
+       seed=st.integers(0, 10_000))
+def test_chunked_chan_statistics_match_two_pass_layernorm(h, mean, std, seed):
+    """The fused GEMM+LayerNorm epilogue never sees a whole row: each warp forms exact two-pass
+    (mean, M2) per 32-column chunk in fp32, merges its chunks, and the 2*CL column slices of a row are merged again after
+    the cluster exchange (Chan et al.).  Emulated in fp32: the merged statistics give the same normalised row as the
+    reference's two-pass LayerNorm to fp32 rounding, also when |mean| >> std (where E[x^2] - E[x]^2 would lose everything)."""
+    rng = np.random.default_rng(seed)
+    f = np.float32
+    x = (rng.standard_normal(h) * std + mean).astype(f)
+    part_cols = 96
+    parts = []
+    for p0 in range(0, h, part_cols):
+        m_loc, m2 = f(0), f(0)
+        for cc, c0 in enumerate(range(p0, p0 + part_cols, 32)):
+            y = x[c0:c0 + 32]
+            mc = f(y.sum(dtype=f) * f(1 / 32))
+            qc = f(((y - mc) ** 2).sum(dtype=f))
+            na, nn = f(32 * cc), f(32 * cc + 32)
+            delta = f(mc - m_loc)
+            m_loc = f(m_loc + delta * f(32) / nn)
+            m2 = f(m2 + qc + delta * delta * (na * f(32) / nn))
+        parts.append((m_loc, m2))
+    mean_all = f(sum(p[0] for p in parts) / f(len(parts)))
+    M2 = f(0)
+    for m_i, m2_i in parts:
+        d = f(m_i - mean_all)
+        M2 = f(M2 + m2_i + f(part_cols) * d * d)
+    eps = f(1e-12)
+    got = (x - mean_all) * f(1.0 / np.sqrt(f(M2 / f(h)) + eps))
+    x64 = x.astype(np.float64)
+    want = (x64 - x64.mean()) / np.sqrt(x64.var() + 1e-12)
+    # the reference computes this in fp32 as well: compare at a few fp32 ulps of the normalised values (|.| <~ 5),
+    # plus the cancellation (x - mean) inherits from fp32 inputs: |mean| * 2^-24 / std
+    tol = 4e-6 + 4 * abs(mean) * 2.0 ** -24 / std
+    assert np.abs(got - want).max() <= tol
