@@ -126,23 +126,26 @@ def test_pipelined_overlaps_and_keeps_order():
     import threading
     import time
     from ragmeup_b200.tokenizer import pipelined
-    seen = []
+    spans = {}
 
     def tok(c):
-        seen.append(("tok", c, threading.current_thread() is threading.main_thread()))
-        time.sleep(0.04)
+        t0 = time.perf_counter()
+        time.sleep(0.05)
+        spans[("tok", c)] = (t0, time.perf_counter(), threading.current_thread() is threading.main_thread())
         return c * 2
 
     def run(t):
-        seen.append(("run", t))
-        time.sleep(0.04)
+        t0 = time.perf_counter()
+        time.sleep(0.05)
+        spans[("run", t)] = (t0, time.perf_counter())
         return t + 1
 
-    t0 = time.time()
     assert pipelined([1, 2, 3, 4], tok, run) == [3, 5, 7, 9]
-    assert time.time() - t0 < 0.29                       # serial would be 0.32 s; overlapped ~0.20 s
-    assert [s[1] for s in seen if s[0] == "run"] == [2, 4, 6, 8]
-    assert not any(s[2] for s in seen if s[0] == "tok")  # tokenisation runs off the calling thread
+    # tokenisation of chunk i+1 starts before the device call of chunk i ends, and runs off the calling thread
+    for c in (1, 2, 3):
+        assert spans[("tok", c + 1)][0] < spans[("run", 2 * c)][1]
+    assert not any(v[2] for k, v in spans.items() if k[0] == "tok")
+    assert [k[1] for k in sorted((k for k in spans if k[0] == "run"), key=lambda k: spans[k][0])] == [2, 4, 6, 8]
     assert pipelined([], tok, run) == [] and pipelined([5], tok, run) == [11]
 
     def bad(c):
