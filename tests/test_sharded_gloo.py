@@ -58,7 +58,10 @@ def _worker(rank, world, port, metric, out):
 @pytest.mark.parametrize("metric", ["l2", "ip"])
 def test_sharded_search_equals_unsharded_gloo(metric):
     world = 2
-    port = 29500 + (os.getpid() % 2000) + (0 if metric == "l2" else 1)
+    import socket
+    with socket.socket() as sk:                      # a port the OS says is free right now
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
     with mp.Manager() as m:
         out = m.dict()
         mp.spawn(_worker, args=(world, port, metric, out), nprocs=world, join=True)
