@@ -309,7 +309,7 @@ def run_gpu(args):
     roof_gemm = None
     if gemm_n:
         ach = gemm_flops_step * args.steps / (gemm_ms * 1e-3) / 1e12
-        roof_gemm = {"kernel": "gemm_f16x3_kernel", "bound": "tensor", "achieved": ach, "peak": tf_sust, "unit": "TFLOP/s",
+        roof_gemm = {"kernel": "gemm_f16x3_kernel + gemm_f16x3_ln_kernel (all encoder projections)", "bound": "tensor", "achieved": ach, "peak": tf_sust, "unit": "TFLOP/s",
                      "frac": ach / tf_sust, "traffic": traffic.get("gemm_dram_bytes_per_launch"),
                      "peak_source": peak_src + " bf16 sustained (timed inside a long step)",
                      "launches": gemm_n, "avg_launch_ms": gemm_ms / gemm_n,
