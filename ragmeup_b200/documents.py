@@ -9,7 +9,7 @@ surface are used instead.
 """
 from __future__ import annotations
 
-from typing import Any, Dict, List, Optional
+from typing import Any, Dict, Optional
 
 try:  # pragma: no cover - not installed in the build image
     from langchain_core.documents import Document  # type: ignore
