@@ -76,6 +76,11 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const void* tmap, in
         "l"(policy)
         : "memory");
 }
+// warm L2 with the box a later tma_load_2d will fetch (no shared memory, no barrier)
+__device__ __forceinline__ void tma_prefetch_l2_2d(const void* tmap, int c0, int c1) {
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1)
+                 : "memory");
+}
 // 3-D tiled tensor load
 __device__ __forceinline__ void tma_load_3d(void* smem_dst, const void* tmap, int c0, int c1, int c2, uint64_t* bar,
                                             uint64_t policy) {
