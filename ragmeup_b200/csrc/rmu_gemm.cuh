@@ -122,7 +122,7 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tAh, const __grid_constant
                 const int mb = tile / n_blks, nb = tile % n_blks;
                 if (p.l2_prefetch && tile + gridDim.x < tiles) {      // study switch: the next tile's A rows start in DRAM
                     const int mb2 = (tile + gridDim.x) / n_blks;
-                    if (mb2 != mb) {
+                    if (mb2 != mb && (tile + gridDim.x) % n_blks == 0) {      // one of the CTAs that will share that row block
                         for (int kb = 0; kb < k_blks; ++kb) {
                             tma_prefetch_l2_2d(&tAh, kb * kGemmBK, mb2 * kGemmBM);
                             tma_prefetch_l2_2d(&tAl, kb * kGemmBK, mb2 * kGemmBM);
