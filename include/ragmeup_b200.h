@@ -51,7 +51,7 @@ uint64_t rmu_launch_count(void);
 
 /* per-kernel-class device timing (CUDA events on the launching stream; used by bench.py for the
  * roofline objects).  classes: 0 scan, 1 finalize, 2 exact scan, 3 merge, 4 gemm, 5 attention,
- * 6 layernorm, 7 embedding, 8 pool/head, 9 misc, 10 scan lead pass (threshold estimation).  rmu_profile_read synchronises the recorded events. */
+ * 6 layernorm, 7 embedding, 8 pool/head, 9 misc, 10 unused (round-1 lead pass).  rmu_profile_read synchronises the recorded events. */
 void rmu_profile_enable(int on);
 void rmu_profile_reset(void);
 int rmu_profile_read(int cls, double* total_ms, int64_t* launches);
@@ -66,6 +66,9 @@ void rmu_index_destroy(rmu_index* idx);
 int rmu_index_reserve(rmu_index* idx, int64_t rows);
 /* append n rows of `dim` fp32; src_is_host selects a host (pinned or pageable) source */
 int rmu_index_add(rmu_index* idx, const float* vecs, int64_t n, int src_is_host, void* stream);
+/* overwrite existing rows in place (PGVector's upsert-on-id, langchain-postgres add_embeddings): rows[n] int64 local row
+ * numbers and vecs [n, dim] fp32, both DEVICE pointers; rows outside [0, size) are ignored */
+int rmu_index_set_rows(rmu_index* idx, const int64_t* rows, const float* vecs, int64_t n, void* stream);
 int64_t rmu_index_size(const rmu_index* idx);
 int rmu_index_dim(const rmu_index* idx);
 int rmu_index_metric(const rmu_index* idx);
@@ -83,7 +86,7 @@ int rmu_index_search(rmu_index* idx, const float* queries, int nq, int k, int64_
 /* same, HOST buffers in and out (H2D + D2H inside the call, synchronises `stream`) */
 int rmu_index_search_host(rmu_index* idx, const float* queries_h, int nq, int k, int64_t id_offset, int mode,
                           float* out_scores_h, int64_t* out_ids_h, void* stream);
-/* diagnostics for the test-suite: raw TF32 accumulators of the first 64-row tile, out [128, 64] */
+/* diagnostics: raw TF32 accumulators of the first 256 rows (one CTA-pair tile) for nq <= 64 queries, out [64, 256] */
 int rmu_debug_scan_tile(rmu_index* idx, const float* queries, int nq, float* out, void* stream);
 /* rows[n] (int64, local row numbers) -> out [n, dim]; feeds MMR (langchain-milvus fetches the
  * fetch_k stored vectors the same way after col.search) */
@@ -92,6 +95,11 @@ int rmu_index_gather(rmu_index* idx, const int64_t* rows, int n, float* out, voi
 /* merge R per-shard result lists (after the NCCL all-gather): [R, nq, k] -> [nq, k] */
 int rmu_topk_merge(const float* scores, const int64_t* ids, int R, int nq, int k, int metric,
                    float* out_scores, int64_t* out_ids, void* stream);
+
+/* the same on the buffer ONE all-gather fills: rank r's scores start at scores + r * rank_stride_scores (elements),
+ * its ids at ids + r * rank_stride_ids, so a per-rank record {scores[nq*k], ids[nq*k]} needs no repacking */
+int rmu_topk_merge_strided(const float* scores, const int64_t* ids, int64_t rank_stride_scores, int64_t rank_stride_ids,
+                           int R, int nq, int k, int metric, float* out_scores, int64_t* out_ids, void* stream);
 
 /* greedy maximal-marginal-relevance re-selection (langchain `maximal_marginal_relevance`,
  * used by as_retriever(search_type="mmr"), server/RAGHelper.py:497-499,533-535):

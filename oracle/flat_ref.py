@@ -64,6 +64,47 @@ def flat_search(q: np.ndarray, x: np.ndarray, k: int, metric: str, id_offset: in
     return scores, ids
 
 
+def flat_search_blocked(q: np.ndarray, x: np.ndarray, k: int, metric: str, id_offset: int = 0,
+                        block: int = 131072) -> Tuple[np.ndarray, np.ndarray]:
+    """The same result as :func:`flat_search` (same fp32 values, same tie rule) for corpora too large to sort
+    whole: the metric is evaluated in row blocks, every block keeps its k best plus everything tied with its
+    k-th value, and the survivors are ordered by (rank, row) exactly as ``flat_search`` orders all rows.
+    Cosine norms are taken per block (row norms do not depend on the block), so the values are bit-identical
+    to ``metric_values`` on the whole matrix up to BLAS blocking of the inner products."""
+    q = np.atleast_2d(np.asarray(q, dtype=np.float32))
+    nq, n = q.shape[0], x.shape[0]
+    missing = np.inf if metric == "l2" else -np.inf
+    scores = np.full((nq, k), missing, dtype=np.float32)
+    ids = np.full((nq, k), -1, dtype=np.int64)
+    if n == 0:
+        return scores, ids
+    keep_v = [[] for _ in range(nq)]
+    keep_r = [[] for _ in range(nq)]
+    for b0 in range(0, n, block):
+        xb = x[b0:b0 + block]
+        vals = metric_values(q, xb, metric)
+        rank = -vals if metric != "l2" else vals
+        nb = xb.shape[0]
+        kk = min(k, nb)
+        for i in range(nq):
+            if nb > kk:
+                kth = np.partition(rank[i], kk - 1)[kk - 1]
+                sel = np.nonzero(rank[i] <= kth)[0]          # the k best and every tie with the k-th
+            else:
+                sel = np.arange(nb)
+            keep_v[i].append(vals[i, sel])
+            keep_r[i].append(sel + b0)
+    kk = min(k, n)
+    for i in range(nq):
+        v = np.concatenate(keep_v[i])
+        r = np.concatenate(keep_r[i])
+        rank = -v if metric != "l2" else v
+        order = np.lexsort((r, rank))[:kk]                    # rank asc, then row asc
+        scores[i, :kk] = v[order]
+        ids[i, :kk] = r[order] + id_offset
+    return scores, ids
+
+
 def shard_merge(scores: np.ndarray, ids: np.ndarray, metric: str) -> Tuple[np.ndarray, np.ndarray]:
     """[R, nq, k] -> [nq, k]: best score first, then lower id; id -1 entries are padding."""
     R, nq, k = scores.shape

@@ -38,6 +38,7 @@ SIGNATURES = {
     "rmu_index_destroy": (None, [C.c_void_p]),
     "rmu_index_reserve": (C.c_int, [C.c_void_p, C.c_int64]),
     "rmu_index_add": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]),
+    "rmu_index_set_rows": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "rmu_index_size": (C.c_int64, [C.c_void_p]),
     "rmu_index_dim": (C.c_int, [C.c_void_p]),
     "rmu_index_metric": (C.c_int, [C.c_void_p]),
@@ -51,6 +52,8 @@ SIGNATURES = {
     "rmu_index_gather": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "rmu_topk_merge": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                  C.c_void_p]),
+    "rmu_topk_merge_strided": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int,
+                                         C.c_void_p, C.c_void_p, C.c_void_p]),
     "rmu_mmr_select": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
                                  C.c_void_p, C.c_void_p]),
     "rmu_bm25_create": (C.c_int, [C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,

@@ -152,6 +152,29 @@ __global__ void row_stats_kernel(const float* __restrict__ x, long long row0, lo
     }
 }
 
+// overwrite existing rows (upsert of a vector store): one warp per row copies the vector and refreshes its statistics
+// (the running maxima only grow: conservative for the certificate)
+__global__ void set_rows_kernel(float* __restrict__ x, const long long* __restrict__ rows, const float* __restrict__ vecs,
+                                long long n_rows, long long n, int D, int metric, float* __restrict__ rscale,
+                                float* __restrict__ rbias, unsigned* __restrict__ max_norm_bits, unsigned* __restrict__ max_dev_bits) {
+    const long long i = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (i >= n_rows) return;
+    const long long r = rows[i];
+    if (r < 0 || r >= n) return;
+    const float* src = vecs + i * D;
+    float* dst = x + r * D;
+    float s = 0.f;
+    for (int d = lane_id(); d < D; d += 32) { const float v = src[d]; dst[d] = v; s = fmaf(v, v, s); }
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane_id() == 0) {
+        const float nrm = sqrtf(s);
+        if (metric == RMU_METRIC_COSINE) rscale[r] = nrm > 0.f ? 1.f / nrm : 0.f;
+        if (metric == RMU_METRIC_L2) rbias[r] = -0.5f * s;
+        atomicMax(max_norm_bits, __float_as_uint(nrm));
+        atomicMax(max_dev_bits, __float_as_uint(fabsf(s - 1.0f)));
+    }
+}
+
 // =====================================================================================================
 // warp-shuffle bitonic sort, descending, of 32*E u64 keys (element i = e*32 + lane)
 // =====================================================================================================
@@ -188,313 +211,6 @@ __device__ __forceinline__ void warp_bitonic_desc(unsigned long long (&v)[E]) {
             }
         }
     }
-}
-
-// Warp-cooperative compaction of the per-thread (= per-query) candidate lists of the lanes that ask
-// for it: sort the list descending, keep the best KEEP, raise that lane's threshold.
-template <int KEEP, int CAP>
-__device__ __forceinline__ void warp_compact(unsigned long long* mybuf, int& cnt, float& tau, bool need) {
-    constexpr int E = CAP / 32;
-    unsigned mask = __ballot_sync(0xffffffffu, need);
-    if (mask == 0) return;
-    __syncwarp();
-    const unsigned lane = lane_id();
-    while (mask) {
-        const int L = __ffs(mask) - 1;
-        mask &= mask - 1;
-        unsigned long long* b = reinterpret_cast<unsigned long long*>(
-            __shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(mybuf), L));
-        const int n = __shfl_sync(0xffffffffu, cnt, L);
-        unsigned long long v[E];
-#pragma unroll
-        for (int e = 0; e < E; ++e) {
-            const int i = e * 32 + lane;
-            v[e] = (i < n) ? b[i] : 0ull;
-        }
-        warp_bitonic_desc<E>(v);
-#pragma unroll
-        for (int e = 0; e < KEEP / 32; ++e) b[e * 32 + lane] = v[e];
-        const unsigned long long kth = __shfl_sync(0xffffffffu, v[KEEP / 32 - 1], 31);
-        if (lane == static_cast<unsigned>(L)) {
-            if (n >= KEEP) { cnt = KEEP; tau = key_score(kth); }
-            // n < KEEP: list is now sorted, count unchanged, threshold unchanged
-        }
-    }
-    __syncwarp();
-}
-
-// =====================================================================================================
-// (1) tcgen05 coarse scan
-// =====================================================================================================
-// list slots per (CTA, query): a compaction leaves KEEP entries and is triggered above CAP - 32, so the
-// capacity must leave real headroom (KEEP = 32 with 64 slots would compact after every single insert)
-__host__ __device__ constexpr int scan_cap(int keep) { return keep < 64 ? 128 : 2 * keep; }
-
-constexpr int kScanQ = 128;        // queries per launch = MMA M = TMEM lanes
-constexpr int kScanACols = 384;    // TMEM columns reserved for the query block (max dim of this path)
-constexpr int kScanThreads = 192;  // warp 0 TMA, warp 1 MMA + TMEM alloc, warps 2..5 epilogue
-
-struct ScanParams {
-    const float* q;        // [nq_total, dim]
-    int q0, nq;            // this launch: queries q0 .. q0+nq-1, nq <= 128
-    int dim;
-    long long n;           // rows in the index
-    int ntiles;            // ceil(n / BN)
-    const float* rscale;   // nullable (cosine)
-    const float* rbias;    // nullable (L2)
-    unsigned long long* lists;  // [gridDim.x][128][CAP]: unsorted candidates of (CTA, query), counts[] of them valid
-    int* counts;                // [gridDim.x][128]
-    float* dbg;            // diagnostics: CTA 0 dumps the raw accumulators of its first tile [128][BN]
-    int ablate;            // profiling only: bit0 skip MMA issue, bit1 skip epilogue work, bit2 skip TMEM loads
-    // threshold exchange: phase 0 = whole range, thresholds start at -inf; phase 1 = only the first `lead`
-    // tiles of every CTA, run with a small KEEP purely to estimate thresholds; phase 2 = whole range again,
-    // every query starting from tau0 = the KEEP-th best key over the union of all CTAs' phase-1 lists (a
-    // subset of the rows, hence a valid lower bound of the final KEEP-th best key).
-    int phase, lead;
-    const float* tau0;     // [nq_total]
-    // K split for 384 < dim <= 768 (the query block only has 384 TMEM columns): pass 1 multiplies columns
-    // [0, 384) and stores raw partial scores, pass 2 multiplies [384, dim) and adds them before thresholding.
-    int kcol0, kdim;       // first column and number of columns of this launch
-    int kpass;             // 0 single pass, 1 write partials only, 2 add partials then continue as usual
-    float* partial;        // [128][npad] raw partial scores of the current query block
-    long long npad;        // row pitch of `partial` (multiple of 32)
-};
-
-// BN rows per tile (= MMA N), NBUF TMEM accumulators, NSLAB pipeline stages, each stage = KD K-blocks
-// (one TMA op; KD > 1 uses the 3-D (32, rows, kblock) tensor map and needs dim % 32 == 0)
-template <int BN, int NBUF, int NSLAB, int KD, bool TMA3D, int KEEP>
-__global__ void __launch_bounds__(kScanThreads, 1)
-scan_tf32_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
-    constexpr int CAP = scan_cap(KEEP);
-    constexpr int SLAB_BYTES = BN * 128 * KD;
-    constexpr uint32_t IDESC = umma_idesc(2 /*tf32*/, 128, BN);
-    static_assert(BN * NBUF <= 512 - kScanACols, "accumulators must fit beside the query block in TMEM");
-
-    extern __shared__ uint8_t smem_raw[];
-    // 1024-byte alignment by OFFSET into the shared array: a pointer round-trip through an integer would lose the
-    // shared address space and turn every staging access into a generic LD/ST
-    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    uint8_t* slabs = smem;
-    float* stage = reinterpret_cast<float*>(smem + NSLAB * SLAB_BYTES);          // [32][128] epilogue staging
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + NSLAB * SLAB_BYTES + 32 * 128 * sizeof(float));
-    uint64_t* empty = full + NSLAB;
-    uint64_t* acc_full = empty + NSLAB;
-    uint64_t* acc_empty = acc_full + NBUF;
-    uint64_t* a_ready = acc_empty + NBUF;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_ready + 1);
-
-    const int warp = threadIdx.x >> 5;
-    const unsigned lane = lane_id();
-    const int KB = (p.kdim + 31) / 32;  // 128-byte K blocks of this launch's column range
-
-    if (threadIdx.x == 0) {
-        for (int i = 0; i < NSLAB; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-        for (int i = 0; i < NBUF; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 128); }
-        mbar_init(a_ready, 128);
-        fence_mbar_init();
-        prefetch_tmap(&tmap);
-    }
-    if (warp == 1) tmem_alloc<512>(tmem_slot);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-
-    // contiguous tile range of this CTA
-    int t0 = static_cast<int>((static_cast<long long>(blockIdx.x) * p.ntiles) / gridDim.x);
-    int t1 = static_cast<int>((static_cast<long long>(blockIdx.x + 1) * p.ntiles) / gridDim.x);
-    if (p.phase == 1) t1 = min(t1, t0 + p.lead);
-
-    // ---- query block -> TMEM (A operand): lane = query, column = dimension, zero padded
-    const int quad = warp & 3;  // TMEM lane quadrant this warp may touch
-    if (warp >= 2) {
-        const int qi = quad * 32 + lane;
-        const float* qrow = (qi < p.nq) ? p.q + static_cast<long long>(p.q0 + qi) * p.dim : nullptr;
-        // dim % 4 == 0 and 16-byte aligned rows (checked by the host): two float4 loads per 8 columns
-        for (int c = 0; c < KB * 4; ++c) {
-            uint32_t r[8];
-            const int d = c * 8;
-            float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
-            if (qrow != nullptr && d < p.kdim) v0 = *reinterpret_cast<const float4*>(qrow + p.kcol0 + d);
-            if (qrow != nullptr && d + 4 < p.kdim) v1 = *reinterpret_cast<const float4*>(qrow + p.kcol0 + d + 4);
-            r[0] = __float_as_uint(v0.x); r[1] = __float_as_uint(v0.y); r[2] = __float_as_uint(v0.z); r[3] = __float_as_uint(v0.w);
-            r[4] = __float_as_uint(v1.x); r[5] = __float_as_uint(v1.y); r[6] = __float_as_uint(v1.z); r[7] = __float_as_uint(v1.w);
-            tmem_st8(tmem_addr(tmem_base, quad * 32, c * 8), r);
-        }
-        tmem_st_wait();
-        tc_fence_before();
-        mbar_arrive(a_ready);                      // the MMA issuer waits for all 128 query rows; TMA streams meanwhile
-    }
-
-    if (warp == 0) {
-        // =========================== TMA producer ===========================
-        if (lane == 0) {
-            int slot = 0;
-            uint32_t phase = 0;
-            for (int t = t0; t < t1; ++t) {
-                for (int kb = 0; kb < KB; kb += KD) {
-                    mbar_wait(&empty[slot], phase ^ 1);
-                    mbar_arrive_expect_tx(&full[slot], SLAB_BYTES);
-                    if (TMA3D) {
-                        tma_load_3d(slabs + slot * SLAB_BYTES, &tmap, 0, t * BN, kb, &full[slot], kEvictFirst);
-                    } else {
-                        // KD boxes of {128 B, BN rows} credited to one barrier (K-blocks past the row end are
-                        // out of bounds and arrive as zeros, still counting their bytes)
-#pragma unroll
-                        for (int kk = 0; kk < KD; ++kk)
-                            tma_load_2d(slabs + slot * SLAB_BYTES + kk * (BN * 128), &tmap, p.kcol0 + (kb + kk) * 32, t * BN,
-                                        &full[slot], kEvictFirst);
-                    }
-                    if (++slot == NSLAB) { slot = 0; phase ^= 1; }
-                }
-            }
-        }
-    } else if (warp == 1) {
-        // =========================== MMA issuer ===========================
-        if (lane == 0) {
-            int slot = 0;
-            uint32_t phase = 0;
-            mbar_wait(a_ready, 0);                 // query block is in TMEM
-            tc_fence_after();
-            for (int t = t0; t < t1; ++t) {
-                const int i = t - t0;
-                const int buf = i % NBUF;
-                const uint32_t use = static_cast<uint32_t>(i / NBUF);
-                mbar_wait(&acc_empty[buf], (use & 1) ^ 1);
-                tc_fence_after();
-                const uint32_t d_addr = tmem_base + kScanACols + buf * BN;
-                for (int kb0 = 0; kb0 < KB; kb0 += KD) {
-                    mbar_wait(&full[slot], phase);
-                    tc_fence_after();
-#pragma unroll
-                    for (int kk = 0; kk < KD; ++kk) {
-                        const int kb = kb0 + kk;
-                        const uint64_t bdesc = umma_desc_sw128_kmajor(smem_u32(slabs + slot * SLAB_BYTES + kk * (BN * 128)));
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            if (kb * 32 + k * 8 < p.kdim && !(p.ablate & 1)) {
-                                mma_tf32_ts(d_addr, tmem_base + kb * 32 + k * 8, bdesc + static_cast<uint64_t>(k * 2),
-                                            IDESC, (kb | k) != 0 ? 1u : 0u);
-                            }
-                        }
-                    }
-                    tc_commit(&empty[slot]);
-                    if (++slot == NSLAB) { slot = 0; phase ^= 1; }
-                }
-                tc_commit(&acc_full[buf]);
-            }
-        }
-    } else {
-        // =========================== epilogue: thread = query ===========================
-        const int qi = quad * 32 + lane;
-        const int te = qi;                       // this thread's column in the staging buffer
-        const bool live = qi < p.nq;
-        unsigned long long* mybuf = p.lists + (static_cast<long long>(blockIdx.x) * kScanQ + qi) * CAP;
-        int cnt = 0;
-        float tau = live ? -INFINITY : INFINITY;
-        if (p.phase == 2 && live) tau = p.tau0[p.q0 + qi];
-        const bool has_sb = (p.rscale != nullptr) || (p.rbias != nullptr);
-        for (int t = t0; t < t1; ++t) {
-            const int i = t - t0;
-            const int buf = i % NBUF;
-            const uint32_t use = static_cast<uint32_t>(i / NBUF);
-            mbar_wait(&acc_full[buf], use & 1);
-            tc_fence_after();
-#pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
-                if (p.ablate & 4) break;
-                uint32_t r[32];
-                tmem_ld32(tmem_addr(tmem_base, quad * 32, kScanACols + buf * BN + c * 32), r);
-                tmem_ld_wait();
-                if (c == BN / 32 - 1) {          // last TMEM read of this tile: hand the accumulator back early
-                    tc_fence_before();
-                    mbar_arrive(&acc_empty[buf]);
-                }
-                if (p.ablate & 2) continue;
-                const long long row0 = static_cast<long long>(t) * BN + c * 32;
-                if (p.kpass == 1) {                       // first K half: park the raw partial scores
-                    if (live && row0 < p.n) {
-                        float4* dst = reinterpret_cast<float4*>(p.partial + static_cast<long long>(qi) * p.npad + row0);
-#pragma unroll
-                        for (int g4 = 0; g4 < 8; ++g4)
-                            dst[g4] = make_float4(__uint_as_float(r[4 * g4]), __uint_as_float(r[4 * g4 + 1]),
-                                                  __uint_as_float(r[4 * g4 + 2]), __uint_as_float(r[4 * g4 + 3]));
-                    }
-                    continue;
-                }
-                if (p.kpass == 2 && live && row0 < p.n) { // second K half: add what the first half parked
-                    const float4* src = reinterpret_cast<const float4*>(p.partial + static_cast<long long>(qi) * p.npad + row0);
-#pragma unroll
-                    for (int g4 = 0; g4 < 8; ++g4) {
-                        const float4 v = src[g4];
-                        r[4 * g4] = __float_as_uint(__uint_as_float(r[4 * g4]) + v.x);
-                        r[4 * g4 + 1] = __float_as_uint(__uint_as_float(r[4 * g4 + 1]) + v.y);
-                        r[4 * g4 + 2] = __float_as_uint(__uint_as_float(r[4 * g4 + 2]) + v.z);
-                        r[4 * g4 + 3] = __float_as_uint(__uint_as_float(r[4 * g4 + 3]) + v.w);
-                    }
-                }
-                if (p.dbg != nullptr && blockIdx.x == 0 && t == t0) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) p.dbg[qi * BN + c * 32 + j] = __uint_as_float(r[j]);
-                }
-                if (row0 < p.n) {
-                    const int valid = static_cast<int>(min(static_cast<long long>(32), p.n - row0));
-                    float key[32];
-                    if (has_sb) {
-                        // per-row scale / bias of this 32-row chunk: one coalesced load, shuffled out
-                        const float sc = (p.rscale != nullptr && static_cast<int>(lane) < valid) ? __ldg(p.rscale + row0 + lane) : 1.f;
-                        const float bi = (p.rbias != nullptr && static_cast<int>(lane) < valid) ? __ldg(p.rbias + row0 + lane) : 0.f;
-#pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            key[j] = fmaf(__uint_as_float(r[j]), __shfl_sync(0xffffffffu, sc, j), __shfl_sync(0xffffffffu, bi, j));
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) key[j] = __uint_as_float(r[j]);
-                    }
-                    // branch-free pass mask (bit j = row j beats this query's running threshold); the
-                    // insert path is entered warp-uniformly and walks only the set bits, reading the
-                    // scores back from a per-thread smem column (no dynamic register indexing).
-                    unsigned m = 0u;
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) m |= (key[j] > tau) ? (1u << j) : 0u;
-                    if (valid < 32) m &= (1u << valid) - 1u;
-                    if (__any_sync(0xffffffffu, m != 0u)) {
-                        float* col = stage + te;
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) col[j * 128] = key[j];
-                        while (m) {
-                            const int j = __ffs(m) - 1;
-                            m &= m - 1;
-                            mybuf[cnt++] = make_key(col[j * 128], static_cast<uint32_t>(row0 + j));
-                        }
-                    }
-                }
-                warp_compact<KEEP, CAP>(mybuf, cnt, tau, cnt > CAP - 32);
-            }
-            if (p.ablate & 4) {
-                tc_fence_before();
-                mbar_arrive(&acc_empty[buf]);
-            }
-        }
-        // final: the list stays as it is (unsorted, <= CAP entries, a superset of this CTA's KEEP best above the
-        // threshold); the selection kernels read `counts` entries.  (Sorting 128 lists per CTA here, one lane at a
-        // time, was a fixed ~0.1 ms tail on every launch: it dominated 1M-row shards.)
-        // Long lists (KEEP >= 128) are still sorted and cut to KEEP here: reading 2 * KEEP entries of every CTA in the
-        // 8-pass radix select of finalize would cost more than it saves.
-        if (p.kpass != 1) {
-            if (KEEP >= 128) {
-                warp_compact<KEEP, CAP>(mybuf, cnt, tau, true);
-                for (int e = cnt; e < KEEP; ++e) mybuf[e] = 0ull;
-            } else {
-                p.counts[blockIdx.x * kScanQ + qi] = cnt;
-            }
-        }
-    }
-
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    if (warp == 1) tmem_dealloc<512>(tmem_base);
 }
 
 // =====================================================================================================
@@ -640,120 +356,58 @@ __device__ __forceinline__ unsigned long long block_radix_select(LoadKey load_ke
     return *s_remaining < 0 ? 1ull : *s_prefix;
 }
 
-// per-query global threshold for phase 2 of the scan: score of the keep-th best key over all CTAs'
-// phase-1 lists (-inf when fewer than keep candidates exist yet)
-__global__ void __launch_bounds__(kSelThreads) select_tau_kernel(const unsigned long long* __restrict__ lists,
-                                                         const int* __restrict__ counts, int nlists, int lstride,
-                                                         int len, int keep, int q0, float* __restrict__ tau0) {
-    __shared__ int hist[256];
-    __shared__ unsigned long long s_prefix;
-    __shared__ int s_remaining, s_ties;
-    const int f = blockIdx.x;
-    const long long total = static_cast<long long>(nlists) * len;
-    const int len_shift = __ffs(len) - 1;
-    auto load_key = [&](long long idx) -> unsigned long long {
-        const long long l = idx >> len_shift;
-        const int e = static_cast<int>(idx & (len - 1));
-        return e < counts[l * kScanQ + f] ? lists[(l * kScanQ + f) * lstride + e] : 0ull;
-    };
-    block_radix_passes(load_key, total, keep, 0, 4, hist, &s_prefix, &s_remaining, &s_ties);   // the score bits suffice
-    if (threadIdx.x == 0) tau0[q0 + f] = s_remaining < 0 ? -INFINITY : key_score(s_prefix);
-}
-
 // =====================================================================================================
-// (2) finalize: global selection of the best KSEL candidates, exact re-score, sort, certificate
+// (3b) merge of the exact scan's per-chunk lists: select the best `ksel` keys, sort, write the top-k
 // =====================================================================================================
 struct FinalizeParams {
-    const unsigned long long* lists;
+    const unsigned long long* lists;   // [nlists][nq_total][len] exact keys, sorted per chunk, zero padded
     int nlists;        // lists per query
-    int qstride;       // queries per list block (128 for the tensor scan, nq_total for the exact scan)
-    int lstride;       // entries between consecutive queries' lists
-    int len;           // entries read per list, pow2 (zero padded, or bounded by counts[])
-    const int* counts; // nullable: valid entries of list (l, query slot) = counts[l * qstride + slot]
-    int ksel;          // candidates to select (<= 1024, <= len for a valid certificate)
-    const float* x; long long n; int dim; int metric;
-    const float* q;    // [nq_total, dim]
-    int q0;            // blockIdx.x + q0 = query (when qmap == nullptr)
-    const int* qmap;   // exact mode: blockIdx.x -> query through qmap
-    const int* nsel;   // exact mode: number of valid blockIdx.x
-    int exact;         // 1: lists hold exact keys, no certificate
-    int unit_rows;     // 1: every row has ||x||^2 = 1 +- 1e-6 and the coarse keys are plain inner products
+    int qstride;       // queries per list block
+    int len;           // entries per list, pow2
+    int ksel;          // keys to keep (<= 1024)
+    int metric;
+    const int* qmap;   // blockIdx.x -> query through qmap (nullable: identity)
+    const int* nsel;   // number of valid blockIdx.x (nullable: all)
     int k;
     long long id_offset;
-    const unsigned* max_norm_bits;
-    float eps_rel;
     float* out_scores; long long* out_ids;   // [nq_total, k]
-    int* flags;        // [nq_total] 1 = certificate failed
 };
 
 __global__ void __launch_bounds__(kSelThreads) finalize_kernel(const FinalizeParams p) {
     __shared__ unsigned long long cand[1024];
-    __shared__ float cval[1024];
     __shared__ int hist[256];
-    __shared__ float red[32];
     __shared__ int s_ncand;
     __shared__ unsigned long long s_prefix;
     __shared__ int s_remaining, s_ties;
-    extern __shared__ float qs[];  // [dim]
 
     const int f = blockIdx.x;
     if (p.nsel != nullptr && f >= *p.nsel) return;
-    const int qg = p.qmap ? p.qmap[f] : p.q0 + f;
-    const int qslot = p.exact ? f : f;  // position of this query inside a list block
+    const int qg = p.qmap ? p.qmap[f] : f;
     const int tid = threadIdx.x;
-
-    float part = 0.f;
-    for (int d = tid; d < p.dim; d += blockDim.x) {
-        float v = p.q[static_cast<long long>(qg) * p.dim + d];
-        qs[d] = v;
-        part = fmaf(v, v, part);
-    }
-    const float qnorm = sqrtf(block_sum(part, red));
 
     const long long total = static_cast<long long>(p.nlists) * p.len;
     const int len_shift = __ffs(p.len) - 1;
     auto load_key = [&](long long idx) -> unsigned long long {
         const long long l = idx >> len_shift;
         const int e = static_cast<int>(idx & (p.len - 1));
-        if (p.counts != nullptr && e >= p.counts[l * p.qstride + qslot]) return 0ull;
-        return p.lists[(l * p.qstride + qslot) * p.lstride + e];
+        return p.lists[(l * p.qstride + f) * p.len + e];
     };
-
     const unsigned long long T = block_radix_select(load_key, total, p.ksel, hist, &s_prefix, &s_remaining, &s_ties);
     if (tid == 0) s_ncand = 0;
     __syncthreads();
-    // ---- collect keys >= T
-    long long nonzero_local = 0;
     for (long long idx = tid; idx < total; idx += blockDim.x) {
         const unsigned long long key = load_key(idx);
-        if (key != 0ull) {
-            ++nonzero_local;
-            if (key >= T) {
-                const int pos = atomicAdd(&s_ncand, 1);
-                if (pos < 1024) cand[pos] = key;
-            }
+        if (key != 0ull && key >= T) {
+            const int pos = atomicAdd(&s_ncand, 1);
+            if (pos < 1024) cand[pos] = key;
         }
     }
-    const float nonzero = block_sum(static_cast<float>(nonzero_local), red);
     __syncthreads();
     const int ncand = min(s_ncand, p.ksel);
-
-    // ---- exact re-score
-    for (int c = tid; c < 1024; c += blockDim.x) {
-        if (c < ncand) {
-            const uint32_t row = key_row(cand[c]);
-            const float v = exact_metric(qs, p.x + static_cast<long long>(row) * p.dim, p.dim, p.metric, qnorm);
-            cval[c] = v;
-            cand[c] = make_key(metric_to_rank(v, p.metric), row);
-        } else {
-            cand[c] = 0ull;
-        }
-    }
+    for (int c = ncand + tid; c < 1024; c += blockDim.x) cand[c] = 0ull;
     int n2 = 32;
     while (n2 < ncand) n2 <<= 1;
     block_bitonic_desc(cand, n2);
-
-    // ---- outputs
     const float missing = p.metric == RMU_METRIC_L2 ? INFINITY : -INFINITY;
     for (int j = tid; j < p.k; j += blockDim.x) {
         float s = missing;
@@ -766,28 +420,9 @@ __global__ void __launch_bounds__(kSelThreads) finalize_kernel(const FinalizePar
         p.out_scores[static_cast<long long>(qg) * p.k + j] = s;
         p.out_ids[static_cast<long long>(qg) * p.k + j] = id;
     }
-    // ---- certificate: every row outside the candidate set has coarse key <= score(T); its exact key is
-    //      at most eps above.  The k-th exact candidate must beat that bound strictly.
-    if (tid == 0 && p.flags != nullptr) {
-        int flag = 0;
-        if (!p.exact && nonzero >= static_cast<float>(p.ksel)) {
-            const int kk = min(p.k, ncand);
-            const float rk = key_score(cand[kk - 1]);  // rank value of the k-th exact result
-            float kth_key;   // in the units of the coarse key
-            float scale;
-            const float xmax = __uint_as_float(*p.max_norm_bits);
-            if (p.metric == RMU_METRIC_IP) { kth_key = rk; scale = qnorm * xmax; }
-            else if (p.metric == RMU_METRIC_COSINE) { kth_key = rk * qnorm; scale = qnorm; }
-            else { kth_key = 0.5f * (qnorm * qnorm + rk) + (p.unit_rows ? 0.5f : 0.f); scale = qnorm * xmax; }  // rk = -dist
-            const float bound = key_score(T);
-            // unit_rows: cosine / L2 keys were scanned as inner products, exact to 1e-6 (||x||^2 = 1 +- 1e-6)
-            const float eps = p.eps_rel * scale + 1e-6f * (1.f + fabsf(kth_key)) + (p.unit_rows ? 4e-6f * (1.f + qnorm) : 0.f);
-            if (!(bound + eps < kth_key)) flag = 1;
-            if (ncand < p.k) flag = 1;
-        }
-        p.flags[qg] = flag;
-    }
 }
+
+#include "rmu_scan.cuh"
 
 // flags[nq] -> qmap (ordered, compacted indices of flagged queries) + nsel; launched with one warp
 __global__ void compact_flags_kernel(const int* __restrict__ flags, int nq, int* __restrict__ qmap, int* __restrict__ nsel) {
@@ -806,6 +441,7 @@ __global__ void compact_flags_kernel(const int* __restrict__ flags, int nq, int*
 // shard merge (after the all-gather of per-shard results): [R, nq, k] -> [nq, k]
 // =====================================================================================================
 __global__ void __launch_bounds__(256) merge_kernel(const float* __restrict__ scores, const long long* __restrict__ ids,
+                                                    long long rstride_s, long long rstride_i,   // elements between ranks
                                                     int R, int nq, int k, int metric, float* __restrict__ out_s,
                                                     long long* __restrict__ out_i) {
     extern __shared__ unsigned char sm[];
@@ -823,9 +459,9 @@ __global__ void __launch_bounds__(256) merge_kernel(const float* __restrict__ sc
         unsigned long long key = 0ull;
         if (t < n) {
             const int r = t / k, j = t % k;
-            const long long src = (static_cast<long long>(r) * nq + qi) * k + j;
-            const long long id = ids[src];
-            const float v = scores[src];
+            const long long src = static_cast<long long>(qi) * k + j;
+            const long long id = ids[r * rstride_i + src];
+            const float v = scores[r * rstride_s + src];
             sid[t] = id;
             sval[t] = v;
             if (id >= 0) key = (static_cast<unsigned long long>(f32_to_ordered(metric_to_rank(v, metric))) << 32) |
@@ -971,11 +607,10 @@ struct rmu_index {
     float* rscale = nullptr;
     float* rbias = nullptr;
     unsigned* max_norm_bits = nullptr;   // [0] max ||x||, [1] max | ||x||^2 - 1 |
-    float* dev_h = nullptr;              // pinned host copy of [1], refreshed after every insert
-    cudaEvent_t stats_ev = nullptr;
     CUtensorMap tmap{};
     int64_t tmap_rows = -1;
-    int tmap_bn = 0;
+    unsigned long long* gmax = nullptr;  // [256][kGroupsMax] threshold exchange of the scan, epoch-tagged (never cleared)
+    unsigned epoch = 0;                  // bumped once per scan launch (under mu)
     // scratch
     void* ws = nullptr;
     size_t ws_bytes = 0;
@@ -1000,70 +635,81 @@ static int ensure_ws(rmu_index* idx, size_t bytes) {
     return RMU_OK;
 }
 
-struct ScanCfg { int bn, nbuf, nslab, keep; };
-
 static int keep_for_k(int k) {
-    // candidates kept per query by the coarse pass: >= 3k where that fits, never above 256
+    // coarse candidates re-scored exactly per query: >= 3k where that fits, never above 256
     if (3 * k <= 64) return 64;
     if (3 * k <= 128) return 128;
     return 256;
 }
 
-template <int BN, int NBUF, int NSLAB, int KD, bool TMA3D, int KEEP>
-static int launch_scan(const CUtensorMap& tmap, const ScanParams& p, int grid, cudaStream_t st) {
-    auto kern = scan_tf32_kernel<BN, NBUF, NSLAB, KD, TMA3D, KEEP>;
-    const size_t smem = static_cast<size_t>(NSLAB) * BN * 128 * KD + 32 * 128 * sizeof(float) + (2 * NSLAB + 2 * NBUF + 1) * 8 + 16 + 1024;
-    static bool attr_set = false;
-    if (!attr_set) {
-        RMU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-        attr_set = true;
-    }
-    ProfScope _ps(p.phase == 1 ? PROF_SCAN_LEAD : PROF_SCAN, st);
-    kern<<<grid, kScanThreads, smem, st>>>(tmap, p);
+// one scan launch: NQ queries (MMA N); CTA pairs keep NQ/2 query rows resident per CTA, single CTAs all NQ
+struct ScanGeom { int nq, nstages, pair; size_t smem; };
+
+static int env_int(const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; }
+static int scan_kd() { static const int v = env_int("RMU_SCAN_KD", 2) == 1 ? 1 : 2; return v; }          // boxes per stage
+static int scan_pair() { static const int v = env_int("RMU_SCAN_PAIR", 0) != 0 ? 1 : 0; return v; }      // cta_group::2 kernel
+static int scan_stages_cap() { static const int v = env_int("RMU_SCAN_STAGES", 0); return v; }           // study: cap the ring
+static int scan_ablate() { static const int v = env_int("RMU_SCAN_ABLATE", 0); return v; }
+
+template <int NQ, int KD, bool PAIR>
+static int scan_launch_t(const CUtensorMap& tx, const CUtensorMap& tq, const ScanParams& p, int grid, size_t smem, cudaStream_t st) {
+    auto kern = scan_rows_kernel<NQ, KD, PAIR>;
+    // per device and cheap: set on every launch (a process may drive several GPUs)
+    RMU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(static_cast<unsigned>(grid));
+    cfg.blockDim = dim3(kScanThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = PAIR ? 2 : 1; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    ProfScope _ps(PROF_SCAN, st);
+    RMU_CUDA(cudaLaunchKernelEx(&cfg, kern, tx, tq, p));
     count_launch();
-    RMU_CHECK_LAUNCH();
     return RMU_OK;
 }
 
-// scan geometry variants {rows per tile, TMEM accumulators, stages, K-blocks per stage, 3-D map}:
-//   0: 64 x 2, 24 x  8 KB (2-D)           1: 128 x 1, 12 x 16 KB (2-D)
-//   2: 64 x 2,  6 x 32 KB (3-D, 4 kb/op)  3: 64 x 2, 12 x 16 KB (3-D, 2 kb/op)   4: 64 x 2, 4 x 48 KB (3-D, 6 kb/op)
-//   5: 128 x 1, 4 stages x 3 boxes of 16 KB   6: 128 x 1, 3 stages x 4 boxes   7: 128 x 1, 2 stages x 6 boxes
-static int scan_variant() {
-    static int v = -1;
-    if (v < 0) {
-        const char* e = getenv("RMU_SCAN_VARIANT");
-        v = e ? atoi(e) : 5;
-        if (v < 0 || v > 7) v = 5;
+static int scan_dispatch(const ScanGeom& g, const CUtensorMap& tx, const CUtensorMap& tq, const ScanParams& p, int grid, cudaStream_t st) {
+    const int kd = scan_kd();
+#define RMU_SCAN_CASE(NQ)                                                                                        \
+    if (g.nq == NQ) {                                                                                            \
+        if (g.pair) return kd == 2 ? scan_launch_t<NQ, 2, true>(tx, tq, p, grid, g.smem, st) : scan_launch_t<NQ, 1, true>(tx, tq, p, grid, g.smem, st);   \
+        return kd == 2 ? scan_launch_t<NQ, 2, false>(tx, tq, p, grid, g.smem, st) : scan_launch_t<NQ, 1, false>(tx, tq, p, grid, g.smem, st);             \
     }
-    return v;
-}
-static bool scan_3d() { const int v = scan_variant(); return v >= 2 && v <= 4; }
-static int scan_bn() { const int v = scan_variant(); return (v == 1 || v >= 5) ? 128 : 64; }
-static int scan_kd() { const int v = scan_variant(); return v == 2 ? 4 : v == 3 ? 2 : v == 4 ? 6 : 1; }   // 3-D box depth
-
-template <int KEEP>
-static int dispatch_variant(const CUtensorMap& tmap, const ScanParams& p, int grid, cudaStream_t st) {
-    switch (scan_variant()) {
-        case 0: return launch_scan<64, 2, 24, 1, false, KEEP>(tmap, p, grid, st);
-        case 1: return launch_scan<128, 1, 12, 1, false, KEEP>(tmap, p, grid, st);
-        case 2: return launch_scan<64, 2, 6, 4, true, KEEP>(tmap, p, grid, st);
-        case 3: return launch_scan<64, 2, 12, 2, true, KEEP>(tmap, p, grid, st);
-        case 4: return launch_scan<64, 2, 4, 6, true, KEEP>(tmap, p, grid, st);
-        case 6: return launch_scan<128, 1, 3, 4, false, KEEP>(tmap, p, grid, st);
-        case 7: return launch_scan<128, 1, 2, 6, false, KEEP>(tmap, p, grid, st);
-        default: return launch_scan<128, 1, 4, 3, false, KEEP>(tmap, p, grid, st);
-    }
+    RMU_SCAN_CASE(128) RMU_SCAN_CASE(64) RMU_SCAN_CASE(32) RMU_SCAN_CASE(16)
+#undef RMU_SCAN_CASE
+    set_error("scan: unsupported geometry");
+    return RMU_ERR_UNSUPPORTED;
 }
 
-static int dispatch_scan(int keep, const CUtensorMap& tmap, const ScanParams& p, int grid, cudaStream_t st) {
-    switch (keep) {
-        case 32: return dispatch_variant<32>(tmap, p, grid, st);
-        case 64: return dispatch_variant<64>(tmap, p, grid, st);
-        case 128: return dispatch_variant<128>(tmap, p, grid, st);
-        case 256: return dispatch_variant<256>(tmap, p, grid, st);
-        default: set_error("scan: unsupported KEEP"); return RMU_ERR_UNSUPPORTED;
-    }
+// largest query block (MMA N) whose resident part fits shared memory at this dimension; 0: dim too large
+static int scan_max_block(int dim) {
+    const int KB = (dim + 31) / 32;
+    const int ncta = scan_pair() ? 2 : 1;
+    int cap = scan_pair() ? kScanMaxQ : 64;
+    while (cap >= 16 && KB * (cap / ncta) * 128 > kScanQOpMax) cap >>= 1;
+    return cap >= 16 ? cap : 0;
+}
+
+// geometry for `rem` queries still to scan
+static ScanGeom scan_geometry(int dim, int rem) {
+    const int KB = (dim + 31) / 32;
+    const int cap = scan_max_block(dim);
+    ScanGeom g{};
+    g.pair = scan_pair();
+    int nq = 16;
+    while (nq < cap && nq < rem) nq <<= 1;
+    const size_t qop = static_cast<size_t>(KB) * (nq / (g.pair ? 2 : 1)) * 128;
+    const size_t stage = static_cast<size_t>(scan_kd()) * kBoxBytes;
+    const size_t budget = 227 * 1024 - 1024 - kScanStateBytes - qop;
+    g.nq = nq;
+    g.nstages = static_cast<int>(std::min<size_t>(budget / stage, kScanMaxStages));
+    if (scan_stages_cap() > 0) g.nstages = std::min(g.nstages, scan_stages_cap());
+    g.smem = 1024 + qop + static_cast<size_t>(g.nstages) * stage + kScanStateBytes;
+    return g;
 }
 
 extern "C" {
@@ -1080,8 +726,8 @@ int rmu_index_create(int dim, int metric, rmu_index** out) {
     }
     cudaError_t e = cudaMalloc(&idx->max_norm_bits, 2 * sizeof(unsigned));
     if (e == cudaSuccess) e = cudaMemset(idx->max_norm_bits, 0, 2 * sizeof(unsigned));
-    if (e == cudaSuccess) e = cudaMallocHost(&idx->dev_h, sizeof(float));
-    if (e == cudaSuccess) { *idx->dev_h = 0.f; e = cudaEventCreateWithFlags(&idx->stats_ev, cudaEventDisableTiming); }
+    if (e == cudaSuccess) e = cudaMalloc(&idx->gmax, sizeof(unsigned long long) * 256 * kGroupsMax);
+    if (e == cudaSuccess) e = cudaMemset(idx->gmax, 0, sizeof(unsigned long long) * 256 * kGroupsMax);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&idx->ws_done, cudaEventDisableTiming);
     if (e != cudaSuccess) { set_error(std::string("rmu_index_create: ") + cudaGetErrorString(e)); delete idx; return RMU_ERR_CUDA; }
     *out = idx;
@@ -1091,10 +737,8 @@ int rmu_index_create(int dim, int metric, rmu_index** out) {
 void rmu_index_destroy(rmu_index* idx) {
     if (!idx) return;
     cudaDeviceSynchronize();
-    cudaFree(idx->x); cudaFree(idx->rscale); cudaFree(idx->rbias); cudaFree(idx->max_norm_bits); cudaFree(idx->ws); cudaFree(idx->hbuf);
+    cudaFree(idx->x); cudaFree(idx->rscale); cudaFree(idx->rbias); cudaFree(idx->max_norm_bits); cudaFree(idx->ws); cudaFree(idx->hbuf); cudaFree(idx->gmax);
     if (idx->ws_done) cudaEventDestroy(idx->ws_done);
-    if (idx->stats_ev) cudaEventDestroy(idx->stats_ev);
-    if (idx->dev_h) cudaFreeHost(idx->dev_h);
     delete idx;
 }
 
@@ -1153,10 +797,22 @@ int rmu_index_add(rmu_index* idx, const float* vecs, int64_t n, int src_is_host,
                                                                           idx->max_norm_bits + 1);
     count_launch();
     RMU_CHECK_LAUNCH();
-    RMU_CUDA(cudaMemcpyAsync(idx->dev_h, idx->max_norm_bits + 1, sizeof(float), cudaMemcpyDeviceToHost, st));
-    RMU_CUDA(cudaEventRecord(idx->stats_ev, st));
     idx->n += n;
     idx->tmap_rows = -1;
+    return RMU_OK;
+}
+
+int rmu_index_set_rows(rmu_index* idx, const int64_t* rows, const float* vecs, int64_t n, void* stream) {
+    if (!idx || n < 0 || (n > 0 && (!rows || !vecs))) { set_error("rmu_index_set_rows: bad argument"); return RMU_ERR_ARG; }
+    if (n == 0) return RMU_OK;
+    std::lock_guard<std::mutex> g(idx->mu);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int wpb = 8;
+    set_rows_kernel<<<static_cast<unsigned>((n + wpb - 1) / wpb), wpb * 32, 0, st>>>(
+        idx->x, reinterpret_cast<const long long*>(rows), vecs, n, idx->n, idx->dim, idx->metric, idx->rscale, idx->rbias,
+        idx->max_norm_bits, idx->max_norm_bits + 1);
+    count_launch();
+    RMU_CHECK_LAUNCH();
     return RMU_OK;
 }
 
@@ -1172,7 +828,16 @@ int rmu_index_clear(rmu_index* idx) {
     idx->n = 0;
     idx->tmap_rows = -1;
     RMU_CUDA(cudaMemset(idx->max_norm_bits, 0, 2 * sizeof(unsigned)));
-    *idx->dev_h = 0.f;
+    return RMU_OK;
+}
+
+// corpus tensor map: boxes of {32 floats, 128 rows}, 128-byte swizzle; idx->mu held
+static int ensure_corpus_tmap(rmu_index* idx) {
+    if (idx->tmap_rows == idx->n) return RMU_OK;
+    int rc = make_tmap_2d(&idx->tmap, idx->x, static_cast<uint64_t>(idx->n), static_cast<uint64_t>(idx->dim),
+                          static_cast<uint64_t>(idx->dim) * sizeof(float), 32, kTileRows, 4);
+    if (rc != RMU_OK) return rc;
+    idx->tmap_rows = idx->n;
     return RMU_OK;
 }
 
@@ -1191,28 +856,24 @@ int rmu_index_search(rmu_index* idx, const float* queries, int nq, int k, int64_
 
     const int D = idx->dim;
     const long long N = idx->n;
-    // tensor scan eligibility: TMA row pitch multiple of 16 B, query block fits TMEM, enough rows, k small
-    // (queries must be 16-byte aligned: the scan loads them as float4)
-    const bool tensor_ok = (D % 4 == 0) && D <= 2 * kScanACols && N >= 16384 && k <= 128 && mode != RMU_SEARCH_EXACT &&
-                           (reinterpret_cast<uintptr_t>(queries) & 15) == 0 &&
-                           (D <= kScanACols || !scan_3d());   // the K-split passes use the 2-D tensor map
-    const bool ksplit = tensor_ok && D > kScanACols;
-    const int keep = keep_for_k(k);                       // tensor: candidates kept per query (>= 3k)
+    // tensor scan eligibility: TMA row pitch multiple of 16 B (queries too: they are loaded by TMA), the resident
+    // query operand fits shared memory (dim <= 3072), enough rows, k small
+    const bool tensor_ok = (D % 4 == 0) && scan_max_block(D) > 0 && N >= 16384 && k <= 128 && mode != RMU_SEARCH_EXACT &&
+                           (reinterpret_cast<uintptr_t>(queries) & 15) == 0 && idx->sms >= 2;
+    const int keep = keep_for_k(k);                       // tensor: coarse candidates re-scored per query (>= 2k)
     int keepx = 32; while (keepx < k) keepx <<= 1;        // exact: per-chunk list length (>= k)
     const int nchunks = static_cast<int>((N + kChunk - 1) / kChunk);
 
     // ---- scratch layout
-    const int grid_scan = idx->sms;
+    const int max_lists = idx->sms * kScanMaxQ;           // (CTA, query) lists of one scan launch
     size_t off = 0;
     auto carve = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~size_t(255); return o; };
     const size_t o_flags = carve(sizeof(int) * nq);
     const size_t o_qmap = carve(sizeof(int) * nq);
     const size_t o_nsel = carve(sizeof(int) * 4);
-    const size_t o_scan = tensor_ok ? carve(sizeof(unsigned long long) * grid_scan * kScanQ * 2 * keep) : 0;
-    const size_t o_tau = carve(sizeof(float) * nq);
-    const size_t o_cnt = tensor_ok ? carve(sizeof(int) * grid_scan * kScanQ) : 0;
-    const long long npad = (N + 31) / 32 * 32;
-    const size_t o_part = ksplit ? carve(sizeof(float) * kScanQ * static_cast<size_t>(npad)) : 0;
+    const size_t o_scan = tensor_ok ? carve(sizeof(unsigned long long) * max_lists * kListCap) : 0;
+    const size_t o_cnt = tensor_ok ? carve(sizeof(int) * max_lists) : 0;
+    const size_t o_floor = tensor_ok ? carve(sizeof(float) * max_lists) : 0;
     const size_t o_exact = carve(sizeof(unsigned long long) * std::max(nchunks, 1) * static_cast<size_t>(nq) * keepx);
     int rc = ensure_ws(idx, off);
     if (rc != RMU_OK) return rc;
@@ -1222,110 +883,52 @@ int rmu_index_search(rmu_index* idx, const float* queries, int nq, int k, int64_
     int* d_nsel = reinterpret_cast<int*>(ws + o_nsel);
     unsigned long long* d_scan = reinterpret_cast<unsigned long long*>(ws + o_scan);
     unsigned long long* d_exact = reinterpret_cast<unsigned long long*>(ws + o_exact);
-    float* d_tau0 = reinterpret_cast<float*>(ws + o_tau);
     int* d_cnt = reinterpret_cast<int*>(ws + o_cnt);
-    float* d_part = reinterpret_cast<float*>(ws + o_part);
+    float* d_floor = reinterpret_cast<float*>(ws + o_floor);
 
-    const size_t qsmem = static_cast<size_t>(D) * sizeof(float);
     int scan_launches = 0;
 
-    if (N == 0) {
-        // nothing to search: all results missing.  Reuse finalize with zero lists.
-        FinalizeParams fp{};
-        fp.lists = d_exact; fp.nlists = 0; fp.qstride = nq; fp.lstride = keepx; fp.len = keepx; fp.ksel = keepx;
-        fp.x = idx->x; fp.n = 0; fp.dim = D; fp.metric = idx->metric; fp.q = queries; fp.q0 = 0; fp.exact = 1;
-        fp.k = k; fp.id_offset = id_offset; fp.max_norm_bits = idx->max_norm_bits; fp.eps_rel = 0.f;
-        fp.out_scores = out_scores; fp.out_ids = reinterpret_cast<long long*>(out_ids); fp.flags = nullptr;
-        finalize_kernel<<<nq, kSelThreads, qsmem, st>>>(fp);
-        count_launch();
-        RMU_CHECK_LAUNCH();
-        RMU_CUDA(cudaEventRecord(idx->ws_done, st));
-        return RMU_OK;
-    }
-
-    // unit-norm corpora (sentence-transformers' Normalize output): cosine and L2 rank exactly like the inner
-    // product, so the scan skips the per-row scale / bias and the certificate absorbs the 1e-6 slack
-    bool unit_rows = false;
-    if (tensor_ok && idx->metric != RMU_METRIC_IP) {
-        RMU_CUDA(cudaEventSynchronize(idx->stats_ev));
-        unit_rows = *idx->dev_h < 1e-6f;
-    }
     if (tensor_ok) {
-        if (idx->tmap_rows != N || idx->tmap_bn != scan_bn()) {
-            if (scan_3d()) {
-                if (D % 32 != 0) { set_error("scan variant needs dim % 32 == 0"); return RMU_ERR_UNSUPPORTED; }
-                rc = make_tmap_rows_kblocks(&idx->tmap, idx->x, static_cast<uint64_t>(N), D / 32, scan_bn(), scan_kd());
-            } else {
-                rc = make_tmap_2d(&idx->tmap, idx->x, static_cast<uint64_t>(N), static_cast<uint64_t>(D),
-                                  static_cast<uint64_t>(D) * sizeof(float), 32, scan_bn(), 4);
-            }
+        rc = ensure_corpus_tmap(idx);
+        if (rc != RMU_OK) return rc;
+        const int ntiles = static_cast<int>((N + kTileRows - 1) / kTileRows);
+        for (int q0 = 0; q0 < nq;) {
+            const ScanGeom geo = scan_geometry(D, nq - q0);
+            const int nql = std::min(nq - q0, geo.nq);
+            const int grid = geo.pair ? 2 * std::min(idx->sms / 2, (ntiles + 1) / 2) : std::min(idx->sms, ntiles);   // one CTA per SM
+            const float* qbase = queries + static_cast<size_t>(q0) * D;
+            CUtensorMap tq;
+            rc = make_tmap_2d(&tq, qbase, static_cast<uint64_t>(nql), static_cast<uint64_t>(D),
+                              static_cast<uint64_t>(D) * sizeof(float), 32, static_cast<uint32_t>(geo.nq / (geo.pair ? 2 : 1)), 4);
             if (rc != RMU_OK) return rc;
-            idx->tmap_rows = N;
-            idx->tmap_bn = scan_bn();
-        }
-        const int ntiles = static_cast<int>((N + scan_bn() - 1) / scan_bn());
-        // one logical scan = one launch, or two when dim > 384 (K split: park partial scores, then finish)
-        auto scan_launch = [&](int keep_x, ScanParams sp, int grid) -> int {
-            sp.partial = d_part; sp.npad = npad;
-            if (!ksplit) {
-                sp.kcol0 = 0; sp.kdim = D; sp.kpass = 0;
-                ++scan_launches;
-                return dispatch_scan(keep_x, idx->tmap, sp, grid, st);
-            }
-            sp.kcol0 = 0; sp.kdim = kScanACols; sp.kpass = 1;
-            int r = dispatch_scan(keep_x, idx->tmap, sp, grid, st);
-            if (r != RMU_OK) return r;
-            sp.kcol0 = kScanACols; sp.kdim = D - kScanACols; sp.kpass = 2;
-            scan_launches += 2;
-            return dispatch_scan(keep_x, idx->tmap, sp, grid, st);
-        };
-        for (int q0 = 0; q0 < nq; q0 += kScanQ) {
             ScanParams sp{};
-            sp.q = queries; sp.q0 = q0; sp.nq = std::min(kScanQ, nq - q0); sp.dim = D; sp.n = N; sp.ntiles = ntiles;
-            sp.rscale = (idx->metric == RMU_METRIC_COSINE && !unit_rows) ? idx->rscale : nullptr;
-            sp.rbias = (idx->metric == RMU_METRIC_L2 && !unit_rows) ? idx->rbias : nullptr;
-            sp.lists = d_scan; sp.counts = d_cnt;
-            { static const char* ab = getenv("RMU_SCAN_ABLATE"); sp.ablate = ab ? atoi(ab) : 0; }
-            const int grid = std::min(grid_scan, ntiles);
-            // threshold exchange (big corpora): a cheap lead pass (first ~1 % of every CTA's tiles, KEEP = 32)
-            // estimates per-query thresholds, then the full pass starts from them, so its epilogue almost
-            // never takes the insert path.  The lead rows are read twice (+2 % traffic).
-            static const int lead_env = [] { const char* e = getenv("RMU_SCAN_LEAD_PCT"); return e ? atoi(e) : -1; }();
-            const int lead_pct = lead_env >= 0 ? lead_env : 1;
-            const int tiles_per_cta = ntiles / grid;
-            constexpr int kLeadKeep = 32;
-            const bool exchange = lead_pct > 0 && tiles_per_cta >= 16 && grid * kLeadKeep >= keep;
-            sp.tau0 = d_tau0;
-            if (exchange) {
-                sp.phase = 1;
-                sp.lead = std::max(2, (tiles_per_cta * lead_pct + 99) / 100);
-                rc = scan_launch(kLeadKeep, sp, grid);
-                if (rc != RMU_OK) return rc;
-                { ProfScope _ps(PROF_FINALIZE, st);
-                select_tau_kernel<<<sp.nq, kSelThreads, 0, st>>>(d_scan, d_cnt, grid, scan_cap(kLeadKeep), scan_cap(kLeadKeep), keep, q0, d_tau0); }
-                count_launch();
-                RMU_CHECK_LAUNCH();
-                sp.phase = 2;
-                rc = scan_launch(keep, sp, grid);
-                if (rc != RMU_OK) return rc;
-            } else {
-                sp.phase = 0;
-                rc = scan_launch(keep, sp, grid);
-                if (rc != RMU_OK) return rc;
+            sp.ablate = scan_ablate();
+            sp.nq = nql; sp.dim = D; sp.n = N; sp.ntiles = ntiles; sp.nstages = geo.nstages; sp.metric = idx->metric;
+            sp.rscale = idx->rscale; sp.rbias = idx->rbias; sp.stats_bits = idx->max_norm_bits;
+            sp.lists = d_scan; sp.counts = d_cnt; sp.floors = d_floor; sp.gmax = idx->gmax;
+            sp.epoch = ++idx->epoch;
+            if (idx->epoch == 0xFFFFFFFFu) {                 // epoch wrap: start over from clean tags
+                RMU_CUDA(cudaMemsetAsync(idx->gmax, 0, sizeof(unsigned long long) * 256 * kGroupsMax, st));
+                idx->epoch = 0;
+                sp.epoch = ++idx->epoch;
             }
-            FinalizeParams fp{};
-            fp.lists = d_scan; fp.nlists = grid; fp.qstride = kScanQ; fp.lstride = scan_cap(keep); fp.ksel = keep;
-            if (keep >= 128) { fp.counts = nullptr; fp.len = keep; }            // sorted, cut to keep, zero padded
-            else { fp.counts = d_cnt; fp.len = scan_cap(keep); }                // raw lists + counts
-            fp.x = idx->x; fp.n = N; fp.dim = D; fp.metric = idx->metric; fp.q = queries; fp.q0 = q0; fp.exact = 0;
-            fp.unit_rows = unit_rows ? 1 : 0;
-            fp.k = k; fp.id_offset = id_offset; fp.max_norm_bits = idx->max_norm_bits;
+            sp.groups = keep / kPubRank;                      // 16 * groups >= keep rows score >= the exchanged threshold
+            if (grid < 2 * sp.groups) sp.groups = 0;          // small grids: lists are cut only by their own floors
+            rc = scan_dispatch(geo, idx->tmap, tq, sp, grid, st);
+            if (rc != RMU_OK) return rc;
+            ++scan_launches;
+            SelectParams fp{};
+            fp.lists = d_scan; fp.counts = d_cnt; fp.floors = d_floor; fp.gmax = idx->gmax;
+            fp.ncl = grid; fp.qb = geo.nq; fp.epoch = sp.epoch; fp.groups = sp.groups; fp.ksel = keep;
+            fp.x = idx->x; fp.n = N; fp.dim = D; fp.metric = idx->metric; fp.q = qbase; fp.q0 = q0;
+            fp.k = k; fp.id_offset = id_offset; fp.stats_bits = idx->max_norm_bits;
             fp.eps_rel = 2.2e-3f;   // > 2^-9: both TF32 operands truncated to 10 mantissa bits
             fp.out_scores = out_scores; fp.out_ids = reinterpret_cast<long long*>(out_ids); fp.flags = d_flags;
             { ProfScope _ps(PROF_FINALIZE, st);
-            finalize_kernel<<<sp.nq, kSelThreads, qsmem, st>>>(fp); }
+            select_rescore_kernel<<<nql, kSel2Threads, static_cast<size_t>(D) * sizeof(float), st>>>(fp); }
             count_launch();
             RMU_CHECK_LAUNCH();
+            q0 += nql;
         }
         compact_flags_kernel<<<1, 32, 0, st>>>(d_flags, nq, d_qmap, d_nsel);
         count_launch();
@@ -1333,33 +936,32 @@ int rmu_index_search(rmu_index* idx, const float* queries, int nq, int k, int64_
     }
 
     if (!tensor_ok || mode == RMU_SEARCH_AUTO) {
-        ExactParams ep{};
-        ep.x = idx->x; ep.n = N; ep.dim = D; ep.metric = idx->metric; ep.q = queries;
-        ep.qmap = tensor_ok ? d_qmap : nullptr; ep.nsel = tensor_ok ? d_nsel : nullptr; ep.nq_total = nq;
-        ep.lists = d_exact; ep.keep = keepx;
-        const int ngroups = (nq + kExactQT - 1) / kExactQT;
-        int gy = tensor_ok ? 1 : std::min(ngroups, std::max(1, (2 * idx->sms + nchunks - 1) / nchunks));
-        gy = std::min(gy, 65535);
-        dim3 eg(static_cast<unsigned>(nchunks), static_cast<unsigned>(gy));
-        const size_t esmem = sizeof(float) * kExactQT * (static_cast<size_t>(D) + kChunk);
-        if (esmem > 200 * 1024) { set_error("rmu_index_search: dim too large for the exact scan"); return RMU_ERR_UNSUPPORTED; }
-        static size_t esmem_set = 0;
-        if (esmem > esmem_set) {
+        FinalizeParams fp{};
+        fp.lists = d_exact; fp.qstride = nq; fp.len = keepx; fp.ksel = keepx; fp.metric = idx->metric;
+        fp.k = k; fp.id_offset = id_offset;
+        fp.out_scores = out_scores; fp.out_ids = reinterpret_cast<long long*>(out_ids);
+        if (N > 0) {
+            ExactParams ep{};
+            ep.x = idx->x; ep.n = N; ep.dim = D; ep.metric = idx->metric; ep.q = queries;
+            ep.qmap = tensor_ok ? d_qmap : nullptr; ep.nsel = tensor_ok ? d_nsel : nullptr; ep.nq_total = nq;
+            ep.lists = d_exact; ep.keep = keepx;
+            const int ngroups = (nq + kExactQT - 1) / kExactQT;
+            int gy = tensor_ok ? 1 : std::min(ngroups, std::max(1, (2 * idx->sms + nchunks - 1) / nchunks));
+            gy = std::min(gy, 65535);
+            dim3 eg(static_cast<unsigned>(nchunks), static_cast<unsigned>(gy));
+            const size_t esmem = sizeof(float) * kExactQT * (static_cast<size_t>(D) + kChunk);
+            if (esmem > 200 * 1024) { set_error("rmu_index_search: dim too large for the exact scan"); return RMU_ERR_UNSUPPORTED; }
             RMU_CUDA(cudaFuncSetAttribute(exact_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(esmem)));
-            esmem_set = esmem;
+            { ProfScope _ps(PROF_EXACT, st);
+            exact_scan_kernel<<<eg, 256, esmem, st>>>(ep); }
+            count_launch();
+            RMU_CHECK_LAUNCH();
+            fp.nlists = nchunks; fp.qmap = ep.qmap; fp.nsel = ep.nsel;
+        } else {
+            fp.nlists = 0;                                // nothing to search: all results missing
         }
         { ProfScope _ps(PROF_EXACT, st);
-        exact_scan_kernel<<<eg, 256, esmem, st>>>(ep); }
-        count_launch();
-        RMU_CHECK_LAUNCH();
-        FinalizeParams fp{};
-        fp.lists = d_exact; fp.nlists = nchunks; fp.qstride = nq; fp.lstride = keepx; fp.len = keepx; fp.ksel = keepx;
-        fp.x = idx->x; fp.n = N; fp.dim = D; fp.metric = idx->metric; fp.q = queries; fp.q0 = 0;
-        fp.qmap = ep.qmap; fp.nsel = ep.nsel; fp.exact = 1;
-        fp.k = k; fp.id_offset = id_offset; fp.max_norm_bits = idx->max_norm_bits; fp.eps_rel = 0.f;
-        fp.out_scores = out_scores; fp.out_ids = reinterpret_cast<long long*>(out_ids); fp.flags = nullptr;
-        { ProfScope _ps(PROF_EXACT, st);
-        finalize_kernel<<<nq, kSelThreads, qsmem, st>>>(fp); }
+        finalize_kernel<<<nq, kSelThreads, 0, st>>>(fp); }
         count_launch();
         RMU_CHECK_LAUNCH();
     }
@@ -1377,29 +979,37 @@ int rmu_index_search(rmu_index* idx, const float* queries, int nq, int k, int64_
     return RMU_OK;
 }
 
-// diagnostics (tests only): raw TF32 accumulators of the first 64-row tile, out [128, 64] device fp32
+// diagnostics: raw TF32 accumulators of the first 256 rows (one pair tile), out [nq <= 64, 256] device fp32
 int rmu_debug_scan_tile(rmu_index* idx, const float* queries, int nq, float* out, void* stream) {
-    if (!idx || !queries || !out || nq <= 0 || nq > kScanQ || idx->n <= 0 || idx->dim % 4 != 0 || idx->dim > kScanACols) {
+    if (!idx || !queries || !out || nq <= 0 || nq > 64 || idx->n <= 0 || idx->dim % 4 != 0 || idx->dim > 384 ||
+        (reinterpret_cast<uintptr_t>(queries) & 15) != 0) {
         set_error("rmu_debug_scan_tile: bad argument");
         return RMU_ERR_ARG;
     }
     std::lock_guard<std::mutex> g(idx->mu);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const size_t dbg_lists = sizeof(unsigned long long) * kScanQ * 2 * 64;
-    int rc = ensure_ws(idx, dbg_lists + sizeof(int) * kScanQ + 1024);
+    RMU_CUDA(cudaStreamWaitEvent(st, idx->ws_done, 0));
+    const size_t lists = sizeof(unsigned long long) * 2 * 64 * kListCap;
+    int rc = ensure_ws(idx, lists + 4 * sizeof(int) * 64 + 1024);
     if (rc != RMU_OK) return rc;
-    if (scan_3d()) rc = make_tmap_rows_kblocks(&idx->tmap, idx->x, static_cast<uint64_t>(idx->n), idx->dim / 32, scan_bn(), scan_kd());
-    else rc = make_tmap_2d(&idx->tmap, idx->x, static_cast<uint64_t>(idx->n), static_cast<uint64_t>(idx->dim),
-                           static_cast<uint64_t>(idx->dim) * sizeof(float), 32, scan_bn(), 4);
+    rc = ensure_corpus_tmap(idx);
     if (rc != RMU_OK) return rc;
-    idx->tmap_rows = idx->n;
-    idx->tmap_bn = scan_bn();
+    ScanGeom geo = scan_geometry(idx->dim, 64);
+    CUtensorMap tq;
+    rc = make_tmap_2d(&tq, queries, static_cast<uint64_t>(nq), static_cast<uint64_t>(idx->dim),
+                      static_cast<uint64_t>(idx->dim) * sizeof(float), 32, static_cast<uint32_t>(geo.nq / (geo.pair ? 2 : 1)), 4);
+    if (rc != RMU_OK) return rc;
     ScanParams sp{};
-    sp.q = queries; sp.q0 = 0; sp.nq = nq; sp.dim = idx->dim; sp.n = idx->n; sp.ntiles = 1;
+    sp.nq = nq; sp.dim = idx->dim; sp.n = idx->n; sp.ntiles = 2; sp.nstages = geo.nstages; sp.metric = RMU_METRIC_IP;
+    sp.stats_bits = idx->max_norm_bits;
     sp.lists = static_cast<unsigned long long*>(idx->ws);
-    sp.counts = reinterpret_cast<int*>(static_cast<uint8_t*>(idx->ws) + dbg_lists);
-    sp.dbg = out; sp.kcol0 = 0; sp.kdim = idx->dim; sp.kpass = 0;
-    return dispatch_scan(64, idx->tmap, sp, 1, st);
+    sp.counts = reinterpret_cast<int*>(static_cast<uint8_t*>(idx->ws) + lists);
+    sp.floors = reinterpret_cast<float*>(sp.counts + 128);
+    sp.gmax = idx->gmax; sp.epoch = ++idx->epoch; sp.groups = 0;
+    sp.dbg = out;
+    rc = scan_dispatch(geo, idx->tmap, tq, sp, 2, st);
+    RMU_CUDA(cudaEventRecord(idx->ws_done, st));
+    return rc;
 }
 
 int rmu_index_search_host(rmu_index* idx, const float* queries_h, int nq, int k, int64_t id_offset, int mode,
@@ -1442,6 +1052,7 @@ int rmu_index_search_host(rmu_index* idx, const float* queries_h, int nq, int k,
 int rmu_index_gather(rmu_index* idx, const int64_t* rows, int n, float* out, void* stream) {
     if (!idx || n < 0 || (n > 0 && (!rows || !out))) { set_error("rmu_index_gather: bad argument"); return RMU_ERR_ARG; }
     if (n == 0) return RMU_OK;
+    std::lock_guard<std::mutex> g(idx->mu);      // a concurrent add may grow (free + reallocate) the corpus
     gather_rows_kernel<<<n, 128, 0, static_cast<cudaStream_t>(stream)>>>(idx->x, idx->n, idx->dim,
                                                                           reinterpret_cast<const long long*>(rows), n, out);
     count_launch();
@@ -1449,8 +1060,8 @@ int rmu_index_gather(rmu_index* idx, const int64_t* rows, int n, float* out, voi
     return RMU_OK;
 }
 
-int rmu_topk_merge(const float* scores, const int64_t* ids, int R, int nq, int k, int metric, float* out_scores,
-                   int64_t* out_ids, void* stream) {
+int rmu_topk_merge_strided(const float* scores, const int64_t* ids, int64_t rank_stride_scores, int64_t rank_stride_ids,
+                           int R, int nq, int k, int metric, float* out_scores, int64_t* out_ids, void* stream) {
     if (R <= 0 || nq < 0 || k <= 0 || !scores || !ids || !out_scores || !out_ids || metric < 0 || metric > 2) {
         set_error("rmu_topk_merge: bad argument");
         return RMU_ERR_ARG;
@@ -1460,17 +1071,20 @@ int rmu_topk_merge(const float* scores, const int64_t* ids, int R, int nq, int k
     if (n > 4096) { set_error("rmu_topk_merge: R*k > 4096"); return RMU_ERR_UNSUPPORTED; }
     int n2 = 32; while (n2 < n) n2 <<= 1;
     const size_t smem = static_cast<size_t>(n2) * 8 + static_cast<size_t>(n) * 8 + static_cast<size_t>(n) * 4;
-    static bool attr_set = false;
-    if (!attr_set) {
-        RMU_CUDA(cudaFuncSetAttribute(merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-        attr_set = true;
-    }
+    RMU_CUDA(cudaFuncSetAttribute(merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     ProfScope _ps(PROF_MERGE, static_cast<cudaStream_t>(stream));
-    merge_kernel<<<nq, 256, smem, static_cast<cudaStream_t>(stream)>>>(scores, reinterpret_cast<const long long*>(ids), R, nq, k,
+    merge_kernel<<<nq, 256, smem, static_cast<cudaStream_t>(stream)>>>(scores, reinterpret_cast<const long long*>(ids),
+                                                                       rank_stride_scores, rank_stride_ids, R, nq, k,
                                                                        metric, out_scores, reinterpret_cast<long long*>(out_ids));
     count_launch();
     RMU_CHECK_LAUNCH();
     return RMU_OK;
+}
+
+int rmu_topk_merge(const float* scores, const int64_t* ids, int R, int nq, int k, int metric, float* out_scores,
+                   int64_t* out_ids, void* stream) {
+    return rmu_topk_merge_strided(scores, ids, static_cast<int64_t>(nq) * k, static_cast<int64_t>(nq) * k, R, nq, k, metric,
+                                  out_scores, out_ids, stream);
 }
 
 int rmu_mmr_select(const float* q, const float* cand, const int32_t* n_cand, int nq, int fetch_k, int dim, int k,

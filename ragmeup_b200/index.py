@@ -83,19 +83,41 @@ class FlatIndex:
                            "rmu_index_add")
                 torch.cuda.current_stream().synchronize()
 
+    def set_rows(self, rows, vectors) -> None:
+        """Overwrite existing rows in place: ``rows`` (ints / int64 tensor, local row numbers), ``vectors`` [n, dim]."""
+        torch = self.torch
+        r = torch.as_tensor(rows, dtype=torch.int64).to(self.device).contiguous().view(-1)
+        v = torch.as_tensor(vectors) if isinstance(vectors, np.ndarray) else vectors.detach()
+        v = v.to(device=self.device, dtype=torch.float32).contiguous()
+        if v.dim() != 2 or v.shape[1] != self.dim or v.shape[0] != r.numel():
+            raise ValueError(f"expected {r.numel()} x {self.dim} vectors, got {tuple(v.shape)}")
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().rmu_index_set_rows(self._h, r.data_ptr(), v.data_ptr(), r.numel(), _lib.stream_ptr()),
+                       "rmu_index_set_rows")
+            r.record_stream(torch.cuda.current_stream())
+            v.record_stream(torch.cuda.current_stream())
+
     def search(self, queries, k: int, id_offset: int = 0, mode: int = MODE_AUTO,
-               want_stats: bool = False) -> Tuple["object", "object"]:
+               want_stats: bool = False, out=None) -> Tuple["object", "object"]:
         """queries CUDA fp32 [nq, dim] -> (scores fp32 [nq, k], ids int64 [nq, k]) on the device.
 
         Scores are the metric values (inner product / cosine similarity / squared L2 distance),
-        best first; missing results (k > len) have id -1."""
+        best first; missing results (k > len) have id -1.  ``out=(scores, ids)``: contiguous CUDA tensors
+        of those shapes to write into (e.g. views of a collective's send buffer)."""
         torch = self.torch
         q = queries.detach().to(device=self.device, dtype=torch.float32).contiguous()
         if q.dim() != 2 or q.shape[1] != self.dim:
             raise ValueError(f"expected [nq, {self.dim}] queries, got {tuple(q.shape)}")
         nq = q.shape[0]
-        scores = torch.empty((nq, k), dtype=torch.float32, device=self.device)
-        ids = torch.empty((nq, k), dtype=torch.int64, device=self.device)
+        if out is None:
+            scores = torch.empty((nq, k), dtype=torch.float32, device=self.device)
+            ids = torch.empty((nq, k), dtype=torch.int64, device=self.device)
+        else:
+            scores, ids = out
+            if (tuple(scores.shape) != (nq, k) or tuple(ids.shape) != (nq, k) or scores.dtype != torch.float32 or
+                    ids.dtype != torch.int64 or not scores.is_contiguous() or not ids.is_contiguous() or
+                    scores.device != self.device or ids.device != self.device):
+                raise ValueError("out= must be contiguous CUDA (fp32 [nq, k], int64 [nq, k]) on the index device")
         stats = (C.c_int32 * 4)() if want_stats else None
         with torch.cuda.device(self.device):
             _lib.check(_lib.lib().rmu_index_search(self._h, q.data_ptr(), nq, int(k), int(id_offset), int(mode),
@@ -146,16 +168,22 @@ class FlatIndex:
 
 
 def topk_merge(scores, ids, metric: str):
-    """[R, nq, k] per-shard results -> merged [nq, k] (``rmu_topk_merge``)."""
+    """[R, nq, k] per-shard results -> merged [nq, k] (``rmu_topk_merge_strided``).  The rank dimension may be
+    strided (views into the receive buffer of one all-gather); the [nq, k] block of each rank must be dense."""
     torch = _lib.require_cuda()
     R, nq, k = scores.shape
-    s = scores.contiguous()
-    i = ids.contiguous()
+
+    def dense_blocks(t):
+        return t if (R == 1 or t[0].is_contiguous()) and t.stride(0) >= nq * k else t.contiguous()
+    s = dense_blocks(scores)
+    i = dense_blocks(ids)
     out_s = torch.empty((nq, k), dtype=torch.float32, device=s.device)
     out_i = torch.empty((nq, k), dtype=torch.int64, device=s.device)
     with torch.cuda.device(s.device):
-        _lib.check(_lib.lib().rmu_topk_merge(s.data_ptr(), i.data_ptr(), R, nq, k, METRICS[metric], out_s.data_ptr(),
-                                             out_i.data_ptr(), _lib.stream_ptr()), "rmu_topk_merge")
+        _lib.check(_lib.lib().rmu_topk_merge_strided(s.data_ptr(), i.data_ptr(), s.stride(0) if R > 1 else nq * k,
+                                                     i.stride(0) if R > 1 else nq * k, R, nq, k, METRICS[metric],
+                                                     out_s.data_ptr(), out_i.data_ptr(), _lib.stream_ptr()),
+                   "rmu_topk_merge_strided")
     return out_s, out_i
 
 

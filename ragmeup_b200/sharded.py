@@ -3,7 +3,7 @@
 The reference has no multi-device path; this is the B200-native equivalent the north star asks for:
 corpus rows are split contiguously over the ranks of a ``torch.distributed`` group (one process per
 GPU), every rank scans only its shard, and ONE all-gather of the per-shard ``[Q, k]`` candidates
-(fp32 score + int64 global id, <= 150 KB per rank) over NCCL/NVLink feeds the on-device merge
+(fp32 scores + int64 global ids as one byte record per rank, <= 150 KB) over NCCL/NVLink feeds the on-device merge
 (``rmu_topk_merge``).  Global ids are ``row + rank offset``, so results equal the unsharded search.
 """
 from __future__ import annotations
@@ -25,6 +25,7 @@ class ShardedFlatIndex:
             from .index import topk_merge
             merge_fn = topk_merge
         self.merge_fn = merge_fn
+        self._xkey, self._x = None, None
         self.offset = 0
         self.total = len(local_index)
         self._sizes = [len(local_index)]
@@ -44,20 +45,45 @@ class ShardedFlatIndex:
         self.offset = sum(self._sizes[: self.rank])
         self.total = sum(self._sizes)
 
+    def _exchange_buffers(self, Q: int, k: int, device):
+        """One send record per rank: {scores fp32 [Q, k] | pad to 16 B | ids int64 [Q, k]} as raw bytes; the receive
+        buffer holds the records of all ranks.  Views into both are created once per (Q, k)."""
+        import torch
+        key = (Q, k, str(device))
+        if self._xkey != key:
+            nb_s = Q * k * 4
+            off_i = (nb_s + 15) // 16 * 16
+            nb = off_i + Q * k * 8
+            mine = torch.empty(nb, dtype=torch.uint8, device=device)
+            allb = torch.empty((self.world, nb), dtype=torch.uint8, device=device)
+            self._x = {
+                "mine": mine, "all": allb.view(-1),       # concatenated form (the gloo backend only takes this one)
+                "s": mine[:nb_s].view(torch.float32).view(Q, k), "i": mine[off_i:].view(torch.int64).view(Q, k),
+                "gs": allb[:, :nb_s].view(torch.float32).view(self.world, Q, k),
+                "gi": allb[:, off_i:].view(torch.int64).view(self.world, Q, k),
+            }
+            self._xkey = key
+        return self._x
+
+    def merge_gathered(self, s, i) -> Tuple[Any, Any]:
+        """This rank's (scores [Q, k], global ids [Q, k]) -> ONE all-gather of the packed records -> merged top-k."""
+        Q, k = s.shape
+        x = self._exchange_buffers(Q, k, s.device)
+        if s.data_ptr() != x["s"].data_ptr():
+            x["s"].copy_(s)
+            x["i"].copy_(i)
+        self.dist.all_gather_into_tensor(x["all"], x["mine"], group=self.group)
+        return self.merge_fn(x["gs"], x["gi"], self.index.metric)
+
     def search(self, queries, k: int) -> Tuple[Any, Any]:
         """Same queries on every rank -> the same merged (scores [Q,k], global ids [Q,k]) on every rank."""
-        import torch
-        s, i = self.index.search(queries, k, id_offset=self.offset)
         if self.world == 1:
-            return s, i
-        Q = s.shape[0]
-        # ONE all-gather: score bits + 64-bit id packed as 3 x int32 per candidate
-        pack = torch.empty((Q, k, 3), dtype=torch.int32, device=s.device)
-        pack[..., 0] = s.contiguous().view(torch.int32)
-        pack[..., 1:] = i.contiguous().view(torch.int32).view(Q, k, 2)
-        parts = [torch.empty_like(pack) for _ in range(self.world)]
-        self.dist.all_gather(parts, pack, group=self.group)
-        allp = torch.stack(parts)                                    # [R, Q, k, 3]
-        gs = allp[..., 0].contiguous().view(torch.float32)
-        gi = allp[..., 1:].contiguous().view(torch.int64).view(self.world, Q, k)
-        return self.merge_fn(gs, gi, self.index.metric)
+            return self.index.search(queries, k, id_offset=self.offset)
+        Q = queries.shape[0]
+        dev = getattr(self.index, "device", queries.device)
+        x = self._exchange_buffers(Q, k, dev)
+        try:                                       # the CUDA index writes straight into the send record
+            s, i = self.index.search(queries, k, id_offset=self.offset, out=(x["s"], x["i"]))
+        except TypeError:                          # look-alikes without out= (CPU tests)
+            s, i = self.index.search(queries, k, id_offset=self.offset)
+        return self.merge_gathered(s, i)

@@ -18,9 +18,22 @@ reference's stores do (``server/server.py:281-284`` reads ``source`` / ``pk``).
 
 The corpus lives in HBM as fp32 ``[N, D]`` inside the C index; texts, ids and metadata stay on the
 host.  All distance arithmetic runs in ``csrc/rmu_index.cu``.
+
+Persistence (``vector_store_uri`` reuse, ``server/.env.template:33``, ``vector_store_initial_load``
+``server/RAGHelper.py:406-434``): the reference's stores keep their rows across process restarts (a
+milvus-lite file at ``connection_args["uri"]`` / a Postgres database).  Here a collection with a storage
+directory appends one segment file per ``add_*`` call (vectors + ids + texts + metadata) and reloads the
+segments when it is constructed again, unless ``drop_old`` is set, which deletes them.  ``Milvus``:
+directory ``<uri>.b200/<collection_name>``; ``PGVector``: ``$RMU_STORE_DIR/<collection_name>`` when that
+variable is set, otherwise the collection only lives in GPU memory (said once on stderr).
 """
 from __future__ import annotations
 
+import glob
+import json
+import os
+import shutil
+import sys
 import threading
 from typing import Any, Dict, Iterable, List, Optional, Sequence, Tuple
 
@@ -66,11 +79,11 @@ class B200VectorStore:
     """Exact brute-force store on one B200.  ``metric``: 'l2' | 'cosine' | 'ip'."""
 
     id_field = "pk"
+    upsert_ids = False          # PGVector: adding an id that exists replaces the row; Milvus inserts a second row
 
     def __init__(self, embedding_function: Any, metric: str = "l2", collection_name: str = "LangChainCollection",
-                 device: Optional[int] = None):
+                 device: Optional[int] = None, storage_dir: Optional[str] = None, drop_old: bool = False):
         self.embedding_func = embedding_function
-        self.embeddings = embedding_function
         self.metric = metric
         self.collection_name = collection_name
         self._device = device
@@ -78,7 +91,19 @@ class B200VectorStore:
         self._pks: List[str] = []
         self._texts: List[str] = []
         self._metas: List[Dict[str, Any]] = []
-        self._lock = threading.Lock()
+        self._row_of: Dict[str, int] = {}
+        self._lock = threading.RLock()
+        self._storage_dir = storage_dir
+        self._segments = 0
+        if storage_dir is not None:
+            if drop_old and os.path.isdir(storage_dir):
+                shutil.rmtree(storage_dir)
+            self._load_segments()
+
+    @property
+    def embeddings(self) -> Any:
+        """LangChain's ``VectorStore.embeddings`` (read-only there as well)."""
+        return self.embedding_func
 
     # ------------------------------------------------------------------ construction (reference forms)
     @classmethod
@@ -109,23 +134,44 @@ class B200VectorStore:
             raise ValueError(f"embedding dimension {dim} does not match the collection ({self.index.dim})")
         return self.index
 
+    def _insert_locked(self, vectors, texts: Sequence[str], metadatas: Sequence[dict], ids: Sequence[str]) -> None:
+        """append (or, with ``upsert_ids``, replace) rows; ``self._lock`` held"""
+        n = len(texts)
+        index = self._ensure_index(int(vectors.shape[1]))
+        new = list(range(n))
+        if self.upsert_ids:
+            last = {pk: j for j, pk in enumerate(ids)}                  # a batch repeating an id keeps its last row
+            upd = [j for j in range(n) if ids[j] in self._row_of and last[ids[j]] == j]
+            new = [j for j in range(n) if ids[j] not in self._row_of and last[ids[j]] == j]
+            if upd:
+                index.set_rows([self._row_of[ids[j]] for j in upd], vectors[upd])
+                for j in upd:
+                    r = self._row_of[ids[j]]
+                    self._texts[r], self._metas[r] = texts[j], dict(metadatas[j])
+        if new:
+            index.add(vectors if len(new) == n else vectors[new])
+            for j in new:
+                self._row_of[ids[j]] = len(self._pks)
+                self._pks.append(ids[j])
+                self._texts.append(texts[j])
+                self._metas.append(dict(metadatas[j]))
+
     def add_embeddings(self, vectors, texts: Sequence[str], metadatas: Optional[Sequence[dict]] = None,
                        ids: Optional[Sequence[str]] = None) -> List[str]:
         """Append pre-computed vectors (CUDA/CPU tensor or numpy [n, D])."""
         n = len(texts)
-        if ids is None:
-            ids = [str(len(self._pks) + i) for i in range(n)]
-        if len(ids) != n or (metadatas is not None and len(metadatas) != n):
+        if (ids is not None and len(ids) != n) or (metadatas is not None and len(metadatas) != n):
             raise ValueError("texts, metadatas and ids must have the same length")
         if n == 0:
             return []
-        dim = int(vectors.shape[1])
-        with self._lock:
-            self._ensure_index(dim).add(vectors)
-            self._pks.extend(str(i) for i in ids)
-            self._texts.extend(texts)
-            self._metas.extend(dict(m) for m in (metadatas or [{} for _ in range(n)]))
-        return [str(i) for i in ids]
+        metas = [dict(m) for m in (metadatas or [{} for _ in range(n)])]
+        texts = list(texts)
+        with self._lock:                                    # default ids, rows and the host tables move together
+            pks = [str(len(self._pks) + i) for i in range(n)] if ids is None else [str(i) for i in ids]
+            self._insert_locked(vectors, texts, metas, pks)
+            if self._storage_dir is not None:
+                self._write_segment(vectors, texts, metas, pks)
+        return pks
 
     def add_texts(self, texts: Iterable[str], metadatas: Optional[List[dict]] = None, ids: Optional[List[str]] = None,
                   batch_size: int = 1000, **_: Any) -> List[str]:
@@ -145,6 +191,30 @@ class B200VectorStore:
         texts = [d.page_content for d in documents]
         metas = [d.metadata for d in documents]
         return self.add_texts(texts, metas, ids=ids, **kwargs)
+
+    # ------------------------------------------------------------------ persistence: one segment per add call
+    def _write_segment(self, vectors, texts, metas, pks) -> None:
+        os.makedirs(self._storage_dir, exist_ok=True)
+        vec = vectors if isinstance(vectors, np.ndarray) else vectors.detach().float().cpu().numpy()
+        table = np.frombuffer(json.dumps({"pks": pks, "texts": texts, "metas": metas}).encode(), dtype=np.uint8)
+        path = os.path.join(self._storage_dir, f"seg_{self._segments:08d}.npz")
+        tmp = path + ".tmp.npz"
+        np.savez(tmp, vectors=np.ascontiguousarray(vec, dtype=np.float32), metric=self.metric, table=table)
+        os.replace(tmp, path)                               # a crash never leaves a half-written segment behind
+        self._segments += 1
+
+    def _load_segments(self) -> None:
+        files = sorted(glob.glob(os.path.join(self._storage_dir, "seg_*.npz")))
+        files = [f for f in files if not f.endswith(".tmp.npz")]
+        for f in files:
+            z = np.load(f, allow_pickle=False)
+            if str(z["metric"]) != self.metric:
+                raise ValueError(f"{f} was written by a {z['metric']} collection, this store is {self.metric}")
+            table = json.loads(bytes(z["table"]).decode())
+            if z["vectors"].size:
+                with self._lock:
+                    self._insert_locked(np.ascontiguousarray(z["vectors"]), table["texts"], table["metas"], table["pks"])
+        self._segments = len(files)
 
     # ------------------------------------------------------------------ search (tensor level)
     def _score_out(self, scores):
@@ -177,6 +247,13 @@ class B200VectorStore:
         meta[self.id_field] = self._pks[row]
         return Document(page_content=self._texts[row], metadata=meta)
 
+    def _docs(self, rows: Sequence[int], scores: Optional[Sequence[float]] = None):
+        """rows -> documents; an insert may be between index.add and the host tables, so wait for it"""
+        with self._lock:
+            if scores is None:
+                return [self._doc(r) for r in rows if r >= 0]
+            return [(self._doc(r), float(sc)) for sc, r in zip(scores, rows) if r >= 0]
+
     def _embed_query_tensor(self, query: str):
         torch = _lib.require_cuda()
         if hasattr(self.embedding_func, "encode_tensor"):
@@ -189,15 +266,13 @@ class B200VectorStore:
         torch = self.index.torch
         q = torch.as_tensor(np.asarray(embedding, dtype=np.float32)[None], device=self.index.device)
         s, i = self.search_tensor(q, k)
-        s, i = s[0].tolist(), i[0].tolist()
-        return [(self._doc(r), float(sc)) for sc, r in zip(s, i) if r >= 0]
+        return self._docs(i[0].tolist(), s[0].tolist())
 
     def similarity_search_with_score(self, query: str, k: int = 4, **kw: Any) -> List[Tuple[Document, float]]:
         if self.index is None or len(self) == 0:
             return []
         s, i = self.search_tensor(self._embed_query_tensor(query), k)
-        s, i = s[0].tolist(), i[0].tolist()
-        return [(self._doc(r), float(sc)) for sc, r in zip(s, i) if r >= 0]
+        return self._docs(i[0].tolist(), s[0].tolist())
 
     def similarity_search(self, query: str, k: int = 4, **kw: Any) -> List[Document]:
         return [d for d, _ in self.similarity_search_with_score(query, k, **kw)]
@@ -223,32 +298,31 @@ class B200VectorStore:
             return []
         torch = self.index.torch
         q = torch.as_tensor(np.asarray(embedding, dtype=np.float32)[None], device=self.index.device)
-        rows = self.mmr_tensor(q, k, fetch_k, lambda_mult)[0].tolist()
-        return [self._doc(r) for r in rows if r >= 0]
+        return self._docs(self.mmr_tensor(q, k, fetch_k, lambda_mult)[0].tolist())
 
     def max_marginal_relevance_search(self, query: str, k: int = 4, fetch_k: int = 20, lambda_mult: float = 0.5,
                                       **_: Any) -> List[Document]:
         if self.index is None or len(self) == 0:
             return []
-        rows = self.mmr_tensor(self._embed_query_tensor(query), k, fetch_k, lambda_mult)[0].tolist()
-        return [self._doc(r) for r in rows if r >= 0]
+        return self._docs(self.mmr_tensor(self._embed_query_tensor(query), k, fetch_k, lambda_mult)[0].tolist())
 
     def as_retriever(self, **kwargs: Any) -> B200Retriever:
         return B200Retriever(self, kwargs.get("search_type", "similarity"), kwargs.get("search_kwargs"))
 
-    # ------------------------------------------------------------------ persistence (vector_store_uri reuse)
+    # ------------------------------------------------------------------ one-file export / import
     def save(self, path: str) -> None:
-        import json
-        vec = self.index.data().cpu().numpy() if self.index is not None else np.zeros((0, 0), np.float32)
-        np.savez(path, vectors=vec, metric=self.metric,
-                 table=np.frombuffer(json.dumps({"pks": self._pks, "texts": self._texts, "metas": self._metas}).encode(),
-                                     dtype=np.uint8))
+        """the whole collection as one ``.npz`` (an export; the segment directory is the live persistence)"""
+        with self._lock:
+            vec = self.index.data().cpu().numpy() if self.index is not None else np.zeros((0, 0), np.float32)
+            table = json.dumps({"pks": self._pks, "texts": self._texts, "metas": self._metas}).encode()
+        np.savez(path, vectors=vec, metric=self.metric, table=np.frombuffer(table, dtype=np.uint8))
 
     @classmethod
     def load(cls, path: str, embedding: Any, **kwargs: Any) -> "B200VectorStore":
-        import json
         z = np.load(path if path.endswith(".npz") else path + ".npz", allow_pickle=False)
         store = cls(embedding, **kwargs)
+        if str(z["metric"]) != store.metric:
+            raise ValueError(f"{path} holds a {z['metric']} collection, {cls.__name__} searches with {store.metric}")
         table = json.loads(bytes(z["table"]).decode())
         if z["vectors"].size:
             store.add_embeddings(np.ascontiguousarray(z["vectors"]), table["texts"], table["metas"], table["pks"])
@@ -257,27 +331,44 @@ class B200VectorStore:
 
 class Milvus(B200VectorStore):
     """Answers to ``langchain_milvus.vectorstores.Milvus`` as constructed at
-    ``server/RAGHelper.py:388-394`` (FLAT / L2; ``drop_old`` clears a reused in-process collection)."""
-
-    _collections: Dict[Tuple[str, str], "Milvus"] = {}
+    ``server/RAGHelper.py:388-394`` (FLAT / L2).  ``connection_args["uri"]`` (the milvus-lite file of the
+    reference, ``vector_store_uri``) names where the collection persists: ``<uri>.b200/<collection_name>``;
+    ``drop_old=True`` deletes what is stored there, otherwise it is loaded."""
 
     def __init__(self, embedding_function: Any, collection_name: str = "LangChainCollection",
                  connection_args: Optional[Dict[str, Any]] = None, drop_old: bool = False, auto_id: bool = False,
                  device: Optional[int] = None, **_: Any):
-        super().__init__(embedding_function, metric="l2", collection_name=collection_name, device=device)
         self.connection_args = dict(connection_args or {})
         self.drop_old = drop_old
         self.auto_id = auto_id
+        uri = self.connection_args.get("uri")
+        storage = None
+        if uri and "://" not in str(uri):                   # a local path, as the reference configures milvus-lite
+            storage = os.path.join(str(uri) + ".b200", collection_name)
+        super().__init__(embedding_function, metric="l2", collection_name=collection_name, device=device,
+                         storage_dir=storage, drop_old=drop_old)
+
+
+_warned_memory_only = False
 
 
 class PGVector(B200VectorStore):
     """Answers to ``langchain_postgres.vectorstores.PGVector`` as constructed at
-    ``server/RAGHelper.py:399-404`` (default distance strategy COSINE, score = 1 - cos)."""
+    ``server/RAGHelper.py:399-404`` (default distance strategy COSINE, score = 1 - cos; adding an id that
+    exists replaces the row).  There is no Postgres behind it: rows persist under ``$RMU_STORE_DIR`` when set."""
 
     id_field = "id"
+    upsert_ids = True
 
     def __init__(self, embeddings: Any = None, collection_name: str = "langchain", connection: Any = None,
-                 use_jsonb: bool = True, device: Optional[int] = None, **_: Any):
-        super().__init__(embeddings, metric="cosine", collection_name=collection_name, device=device)
+                 use_jsonb: bool = True, pre_delete_collection: bool = False, device: Optional[int] = None, **_: Any):
+        global _warned_memory_only
         self.connection = connection
         self.use_jsonb = use_jsonb
+        root = os.environ.get("RMU_STORE_DIR")
+        if not root and not _warned_memory_only:
+            print("ragmeup_b200.PGVector: RMU_STORE_DIR is not set, the collection lives in GPU memory only "
+                  "(rows are not kept across restarts)", file=sys.stderr)
+            _warned_memory_only = True
+        super().__init__(embeddings, metric="cosine", collection_name=collection_name, device=device,
+                         storage_dir=os.path.join(root, collection_name) if root else None, drop_old=pre_delete_collection)

@@ -88,9 +88,9 @@ def test_tensor_scan_equals_exact_and_oracle(cuda, metric, n, nq, k):
 
 @pytest.mark.parametrize("metric", ["ip", "cosine", "l2"])
 @pytest.mark.parametrize("dim,n,nq,k", [(768, 20_000, 5, 10), (400, 17_000, 130, 20), (768, 33_000, 64, 50)])
-def test_k_split_scan_for_wide_vectors(cuda, metric, dim, n, nq, k):
-    """384 < dim <= 768 (bge-base 768-d, config 5): the tensor scan runs two K passes (partial scores parked
-    in HBM); results must still be bit-identical to the exact fp32 scan"""
+def test_wide_vectors_on_the_tensor_scan(cuda, metric, dim, n, nq, k):
+    """384 < dim <= 768 (bge-base 768-d, config 5): fewer queries per CTA (the resident query operand must fit shared
+    memory), clusters with TMA multicast make up for it; results must still be bit-identical to the exact fp32 scan"""
     from ragmeup_b200.index import MODE_AUTO, MODE_EXACT
     g = torch.Generator(device="cuda").manual_seed(dim + n)
     x = torch.nn.functional.normalize(torch.randn(n, dim, device="cuda", generator=g), dim=1)
@@ -102,7 +102,7 @@ def test_k_split_scan_for_wide_vectors(cuda, metric, dim, n, nq, k):
     ix = _idx(cuda, x, metric)
     s0, i0 = ix.search(q, k, mode=MODE_EXACT)
     s1, i1 = ix.search(q, k, mode=MODE_AUTO, want_stats=True)
-    assert ix.last_stats[1] >= 2                      # two launches per logical scan
+    assert ix.last_stats[1] >= 1                      # the tcgen05 scan ran
     assert (i0 == i1).all() and (s0 == s1).all()
     _check_topk_fp64(s1, i1, q.cpu().numpy(), x.cpu().numpy(), k, metric)
 
