@@ -1,0 +1,353 @@
+// Self-attention on tcgen05 / TMEM / TMA (sm_100a).  Included by rmu_encoder.cu inside namespace rmu.
+//
+// Stands behind the eager attention of the reference's encoders (transformers BertSelfAttention,
+// modeling_bert.py:114-140,168-208: softmax(Q K^T / sqrt(d_h)) V per head), reached through
+// HuggingFaceEmbeddings.embed_* (server/RAGHelper_local.py:114-117) and HuggingFaceCrossEncoder.score
+// (server/RAGHelper.py:483-486, server/ScoredCrossEncoderReranker.py:42).
+//
+// One work unit = (sequence, head, block of 128 query rows); all keys of the sequence (<= 256 - d_h) are handled
+// in ONE score tile, so the softmax is the plain two-pass form (no running rescale).  Q (pre-scaled by
+// log2(e) / sqrt(d_h)), K and V arrive as the split fp16 planes [T, 3H] the QKV GEMM epilogue wrote; every
+// product keeps the 3-term split (hi*hi + lo*hi + hi*lo, fp32 accumulate) that holds 1e-3 parity with fp32.
+//
+//   S[128 x keys] = Q K^T     tcgen05.mma.kind::f16, M = 128, N = keys (16-aligned), K = d_h; operands are TMA boxes of
+//                             {d_h halves, rows} (SWIZZLE_64B for d_h = 32, SWIZZLE_128B for 64); S lives in TMEM.
+//   P = exp2(S - rowmax)      softmax warps, thread = row = TMEM lane: two passes of tcgen05.ld over S; P is split into
+//                             fp16 hi / lo, packed two keys per 32-bit column and written back IN PLACE with tcgen05.st:
+//                             the 32 fp32 columns of a 32-key chunk become 16 columns of P_hi + 16 columns of P_lo.
+//   O[128 x d_h] = P V        A operand straight from TMEM (no shared-memory round trip for P), B = the V box as it
+//                             landed ([key][d_h], i.e. MN-major: no transposed copy of V is ever made), O in TMEM.
+//   ctx = O / rowsum          read back with tcgen05.ld, split to planes, stored as 64/128-byte row segments.
+//
+// Persistent CTAs (one per SM) keep TWO units in flight: while softmax group g works on unit i, the tensor core
+// already computes S of unit i+1 into the other TMEM buffer and the TMA warp prefetches units i+2.. into a ring of
+// operand slots, so the CUDA-core softmax (the real cost: exp2, hi/lo split, ~8 instructions per score) never waits
+// for loads or MMAs.
+// The S = Q K^T and O = P V instruction streams are issued by two different threads: S of unit i+2 only waits for the
+// TMEM buffer (P V of unit i done), P V of unit i only for its softmax; issued by one thread in program order, each P V
+// sat behind the other group's read-out and the two groups ran in lockstep (measured: 390 us per layer call, the same
+// as the mma.sync kernel, with 38 % of all warp samples waiting for O).
+//   warp 0: TMA producer   warp 1: S issuer + TMEM allocator   warp 2: P V issuer   warps 3-6: softmax group 0   warps 7-10: group 1
+#pragma once
+
+constexpr int kAtcThreads = 352;
+constexpr int kAtcRows = 128;                 // query rows per unit = MMA M
+constexpr int kAtcBufCols = 256;              // TMEM columns per in-flight unit: S / P from 0, O in the last d_h columns
+constexpr int kAtcMaxSlots = 3;
+constexpr int kAtcMaxChunks = 8;             // 32-key chunks of a score tile (<= 256 keys)
+constexpr int kAtcStateBytes = 512;          // mbarriers behind the operand slots
+
+struct AtcParams {
+    const int* cu;          // [B + 1] token offsets
+    int B, heads, H;        // H = hidden = heads * d_h
+    int row_tiles;          // ceil(max_seqlen / 128)
+    int kp;                 // keys per operand slot: max_seqlen rounded up to 64
+    int nslots;             // operand slots in shared memory (1..3)
+    int nacc;               // O accumulators per unit: 3 (one per product term; needs keys <= 256 - 3 d_h) or 1
+    __half* ctx_hi; __half* ctx_lo;   // [T, H]
+};
+
+// shared-memory matrix descriptor, 8-row (or 8-key) groups `sbo` bytes apart; layout 2 = SWIZZLE_128B, 4 = SWIZZLE_64B
+__device__ __forceinline__ uint64_t atc_desc(uint32_t smem_addr, uint32_t sbo, uint32_t layout) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFF);
+    d |= static_cast<uint64_t>(1) << 16;
+    d |= static_cast<uint64_t>(sbo >> 4) << 32;
+    d |= static_cast<uint64_t>(1) << 46;
+    d |= static_cast<uint64_t>(layout) << 61;
+    return d;
+}
+
+// D[tmem] (+)= A[tmem, fp16 packed two per column] * B[smem], fp32 accumulate
+__device__ __forceinline__ void mma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+          "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+        : "memory");
+}
+
+__device__ __forceinline__ float atc_exp2(float x) {   // ex2.approx: 2 ulp, exp2(-inf) = +0
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// (a, b) -> packed fp16 pair of the high parts and of the residuals (a - hi(a), b - hi(b))
+__device__ __forceinline__ void atc_split_pack(float a, float b, uint32_t& hi, uint32_t& lo) {
+    const __half2 h = __floats2half2_rn(a, b);
+    const float2 hf = __half22float2(h);
+    const __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
+// unit u of the grid-stride enumeration -> (sequence, row tile, head); false when the row tile lies past the sequence
+struct AtcUnit { int b, rt, h, t0, S; };
+__device__ __forceinline__ bool atc_unit(const AtcParams& p, int u, AtcUnit& o) {
+    o.h = u % p.heads;
+    const int br = u / p.heads;
+    o.rt = br % p.row_tiles;
+    o.b = br / p.row_tiles;
+    o.t0 = __ldg(p.cu + o.b);
+    o.S = __ldg(p.cu + o.b + 1) - o.t0;
+    return o.rt * kAtcRows < o.S;
+}
+
+template <int DH>
+__global__ void __launch_bounds__(kAtcThreads, 1)
+attention_tc_kernel(const __grid_constant__ CUtensorMap tq_hi, const __grid_constant__ CUtensorMap tq_lo,
+                    const __grid_constant__ CUtensorMap tk_hi, const __grid_constant__ CUtensorMap tk_lo, const AtcParams p) {
+    constexpr int ROWB = DH * 2;                           // bytes of one operand row (64 or 128)
+    constexpr uint32_t LAYOUT = DH == 32 ? 4u : 2u;        // SWIZZLE_64B / SWIZZLE_128B
+    constexpr uint32_t SBO = 8 * ROWB;                     // 8 rows (or 8 keys) per swizzle group
+    constexpr int QBYTES = kAtcRows * ROWB;                // one plane of the Q tile
+    constexpr int KS = DH / 16;                            // MMA K steps over d_h
+    // O accumulators sit at the end of a TMEM buffer.  With N = d_h = 32 one MMA lasts 16 cycles, far less than the
+    // tensor pipe's latency, and MMAs that accumulate into the SAME columns run back to back at that latency (measured:
+    // ~57 cycles each, 1700 cycles for the 30 MMAs of a 147-key unit, with the softmax warps waiting for O 36 % of the
+    // time).  So each product term (P_hi V_hi, P_lo V_hi, P_hi V_lo) gets its own accumulator when the columns allow it:
+    // three independent chains interleave in the pipe, and the read-out adds them up.
+    const int OCOL = kAtcBufCols - p.nacc * DH;
+    // O = P V: A from TMEM (K-major), B = V as it lies in shared memory ([key][d_h]): MN-major -> bit 16
+    constexpr uint32_t IDESC_O = umma_idesc(0 /*f16*/, kAtcRows, DH) | (1u << 16);
+
+    extern __shared__ uint8_t atc_smem_raw[];
+    uint8_t* smem = atc_smem_raw + ((1024u - (smem_u32(atc_smem_raw) & 1023u)) & 1023u);
+    const int kbytes = p.kp * ROWB;                        // one plane of K (or V) of a slot
+    const int slot_bytes = 2 * QBYTES + 4 * kbytes;        // Qh Ql Kh Kl Vh Vl
+    uint8_t* state = smem + p.nslots * slot_bytes;
+    uint64_t* load_full = reinterpret_cast<uint64_t*>(state);
+    uint64_t* load_empty = load_full + kAtcMaxSlots;
+    uint64_t* s_full = load_empty + kAtcMaxSlots;          // [2] S of buffer g is complete
+    uint64_t* p_full = s_full + 2;                         // [2][8] 32-key chunk c of P in buffer g is written (one barrier per chunk:
+                                                           // a group that runs ahead of the P V issuer cannot lap a phase)
+    uint64_t* o_full = p_full + 2 * kAtcMaxChunks;         // [2] O of buffer g is complete
+    uint64_t* s_free = o_full + 2;                         // [2] the P V MMAs that read buffer g have completed
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_free + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const unsigned lane = lane_id();
+    const int nunits = p.B * p.row_tiles * p.heads;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < p.nslots; ++i) { mbar_init(&load_full[i], 1); mbar_init(&load_empty[i], 1); }
+        for (int g = 0; g < 2; ++g) { mbar_init(&s_full[g], 1); for (int c = 0; c < kAtcMaxChunks; ++c) mbar_init(&p_full[g * kAtcMaxChunks + c], 1); mbar_init(&o_full[g], 1); mbar_init(&s_free[g], 1); }
+        fence_mbar_init();
+        prefetch_tmap(&tq_hi); prefetch_tmap(&tq_lo); prefetch_tmap(&tk_hi); prefetch_tmap(&tk_lo);
+    }
+    if (warp == 1) tmem_alloc<512>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // =========================== TMA producer ===========================
+        if (lane == 0) {
+            int i = 0;
+            for (int u = blockIdx.x; u < nunits; u += gridDim.x) {
+                AtcUnit un;
+                if (!atc_unit(p, u, un)) continue;
+                const int slot = i % p.nslots;
+                const uint32_t use = static_cast<uint32_t>(i / p.nslots);
+                mbar_wait(&load_empty[slot], (use & 1) ^ 1);
+                const int nkb = (un.S + 63) >> 6;                       // 64-key boxes of this sequence
+                uint8_t* sb = smem + slot * slot_bytes;
+                mbar_arrive_expect_tx(&load_full[slot], static_cast<uint32_t>(2 * QBYTES + 4 * nkb * 64 * ROWB));
+                const int qrow = un.t0 + un.rt * kAtcRows, qcol = un.h * DH;
+                tma_load_2d(sb, &tq_hi, qcol, qrow, &load_full[slot], kEvictNormal);
+                tma_load_2d(sb + QBYTES, &tq_lo, qcol, qrow, &load_full[slot], kEvictNormal);
+                for (int kb = 0; kb < nkb; ++kb) {
+                    const int krow = un.t0 + kb * 64;
+                    uint8_t* kd = sb + 2 * QBYTES + kb * 64 * ROWB;
+                    tma_load_2d(kd, &tk_hi, p.H + qcol, krow, &load_full[slot], kEvictNormal);
+                    tma_load_2d(kd + kbytes, &tk_lo, p.H + qcol, krow, &load_full[slot], kEvictNormal);
+                    tma_load_2d(kd + 2 * kbytes, &tk_hi, 2 * p.H + qcol, krow, &load_full[slot], kEvictNormal);
+                    tma_load_2d(kd + 3 * kbytes, &tk_lo, 2 * p.H + qcol, krow, &load_full[slot], kEvictNormal);
+                }
+                ++i;
+            }
+        }
+    } else if (warp == 1) {
+        // =========================== S = Q K^T issuer ===========================
+        if (lane == 0) {
+            int i = 0;
+            for (int u = blockIdx.x; u < nunits; u += gridDim.x) {
+                AtcUnit un;
+                if (!atc_unit(p, u, un)) continue;
+                const int g = i & 1;
+                const uint32_t use = static_cast<uint32_t>(i >> 1);
+                const int slot = i % p.nslots;
+                mbar_wait(&load_full[slot], static_cast<uint32_t>(i / p.nslots) & 1);
+                mbar_wait(&s_free[g], (use & 1) ^ 1);            // P V of the unit two back no longer reads this buffer
+                tc_fence_after();
+                const uint8_t* sb = smem + slot * slot_bytes;
+                const uint32_t qh = smem_u32(sb), ql = qh + QBYTES, kh = qh + 2 * QBYTES, kl = kh + kbytes;
+                const uint32_t idesc_s = umma_idesc(0 /*f16*/, kAtcRows, ((un.S + 15) >> 4) << 4);
+                const uint32_t d_addr = tmem_base + g * kAtcBufCols;
+#pragma unroll
+                for (int term = 0; term < 3; ++term) {
+                    const uint32_t a = term == 1 ? ql : qh, b = term == 2 ? kl : kh;
+#pragma unroll
+                    for (int k = 0; k < KS; ++k)
+                        mma_f16_ss(d_addr, atc_desc(a + k * 32, SBO, LAYOUT), atc_desc(b + k * 32, SBO, LAYOUT), idesc_s,
+                                   (term | k) != 0 ? 1u : 0u);
+                }
+                tc_commit(&s_full[g]);
+                ++i;
+            }
+        }
+    } else if (warp == 2) {
+        // =========================== O = P V issuer ===========================
+        if (lane == 0) {
+            int i = 0;
+            for (int u = blockIdx.x; u < nunits; u += gridDim.x) {
+                AtcUnit un;
+                if (!atc_unit(p, u, un)) continue;
+                const int g = i & 1;
+                const uint32_t use = static_cast<uint32_t>(i >> 1);
+                const int slot = i % p.nslots;
+                const uint8_t* sb = smem + slot * slot_bytes;
+                const uint32_t vh = smem_u32(sb + 2 * QBYTES + 2 * kbytes), vl = vh + kbytes;
+                const uint32_t pbase = tmem_base + g * kAtcBufCols;
+                const uint32_t d_addr = pbase + OCOL;
+                const uint32_t d1 = p.nacc == 3 ? d_addr + DH : d_addr, d2 = p.nacc == 3 ? d_addr + 2 * DH : d_addr;
+                const int nk16 = (un.S + 15) >> 4;
+                const int nchunk = (un.S + 31) >> 5;
+                // P arrives 32 keys at a time (the same warps read O of the unit two back out before they wrote any of it):
+                // the MMAs of a chunk are issued while the softmax warps are still working on the next one
+                for (int c = 0; c < nchunk; ++c) {
+                    mbar_wait(&p_full[g * kAtcMaxChunks + c], use & 1);
+                    tc_fence_after();
+                    for (int j16 = 2 * c; j16 < min(2 * c + 2, nk16); ++j16) {
+                        const uint32_t a_hi = pbase + 32 * c + 8 * (j16 & 1), a_lo = a_hi + 16;
+                        const uint64_t bh = atc_desc(vh + j16 * 16 * ROWB, SBO, LAYOUT), bl = atc_desc(vl + j16 * 16 * ROWB, SBO, LAYOUT);
+                        const uint32_t acc = j16 != 0 ? 1u : 0u;
+                        mma_f16_ts(d_addr, a_hi, bh, IDESC_O, acc);
+                        mma_f16_ts(d1, a_lo, bh, IDESC_O, p.nacc == 3 ? acc : 1u);
+                        mma_f16_ts(d2, a_hi, bl, IDESC_O, p.nacc == 3 ? acc : 1u);
+                    }
+                }
+                tc_commit(&o_full[g]);
+                tc_commit(&s_free[g]);
+                tc_commit(&load_empty[slot]);                    // the operand slot is free once these MMAs have read it
+                ++i;
+            }
+        }
+    } else {
+        // =========================== softmax + output: thread = query row ===========================
+        const int grp = (warp - 3) >> 2;                         // which of the two in-flight units this warp serves
+        const int quad = warp & 3;                               // TMEM lane quadrant this warp may touch
+        const int r = quad * 32 + static_cast<int>(lane);        // row of the unit
+        const int gtid = (warp - 3 - 4 * grp) * 32 + static_cast<int>(lane);   // thread index inside the group
+        int i = 0;
+        for (int u = blockIdx.x; u < nunits; u += gridDim.x) {
+            AtcUnit un;
+            if (!atc_unit(p, u, un)) continue;
+            if ((i & 1) != grp) { ++i; continue; }
+            const uint32_t use = static_cast<uint32_t>(i >> 1);
+            ++i;
+            const uint32_t tb = tmem_addr(tmem_base, quad * 32, grp * kAtcBufCols);
+            const int S = un.S;
+            const int nchunk = (S + 31) >> 5;
+            const bool warp_live = un.rt * kAtcRows + quad * 32 < S;      // any row of this warp inside the sequence
+            mbar_wait(&s_full[grp], use & 1);
+            tc_fence_after();
+            float l = 0.f, m = -INFINITY;
+            if (warp_live) {
+                // ---- pass 1: row maximum
+                for (int c = 0; c < nchunk; ++c) {
+                    uint32_t s[32];
+                    tmem_ld32(tb + c * 32, s);
+                    tmem_ld_wait();
+                    if (c * 32 + 32 <= S) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) m = fmaxf(m, __uint_as_float(s[j]));
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) m = fmaxf(m, c * 32 + j < S ? __uint_as_float(s[j]) : -INFINITY);
+                    }
+                }
+            }
+            // ---- pass 2: P = exp2(S - m) (scores are pre-scaled by log2 e), split, packed back in place; every chunk is
+            // handed to the P V issuer as soon as all four warps of the group have written it
+            for (int c = 0; c < nchunk; ++c) {
+                if (warp_live) {
+                    uint32_t s[32];
+                    tmem_ld32(tb + c * 32, s);
+                    tmem_ld_wait();
+                    uint32_t ph[16], pl[16];
+                    const bool tail = c * 32 + 32 > S;
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        float a = atc_exp2(__uint_as_float(s[2 * j]) - m), b = atc_exp2(__uint_as_float(s[2 * j + 1]) - m);
+                        if (tail) {                                  // keys past the sequence end: stale columns, P = 0
+                            if (c * 32 + 2 * j >= S) a = 0.f;
+                            if (c * 32 + 2 * j + 1 >= S) b = 0.f;
+                        }
+                        l += a + b;
+                        atc_split_pack(a, b, ph[j], pl[j]);
+                    }
+                    tmem_st16(tb + c * 32, ph);
+                    tmem_st16(tb + c * 32 + 16, pl);
+                    tmem_st_wait();
+                }
+                tc_fence_before();
+                bar_sync_named(1 + grp, 128);
+                if (gtid == 0) mbar_arrive(&p_full[grp * kAtcMaxChunks + c]);
+            }
+            // ---- O / l -> split planes
+            mbar_wait(&o_full[grp], use & 1);
+            tc_fence_after();
+            const int row = un.rt * kAtcRows + r;
+            if (warp_live) {
+                const float inv = 1.0f / l;
+#pragma unroll
+                for (int c = 0; c < DH / 32; ++c) {
+                    uint32_t o[32];
+                    tmem_ld32(tb + OCOL + c * 32, o);
+                    tmem_ld_wait();
+                    if (p.nacc == 3) {                               // the three product terms were accumulated separately
+                        uint32_t o1[32], o2[32];
+                        tmem_ld32(tb + OCOL + DH + c * 32, o1);
+                        tmem_ld32(tb + OCOL + 2 * DH + c * 32, o2);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            o[j] = __float_as_uint(__uint_as_float(o[j]) + (__uint_as_float(o1[j]) + __uint_as_float(o2[j])));
+                    }
+                    if (row < S) {
+                        uint32_t oh[16], ol[16];
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            atc_split_pack(__uint_as_float(o[2 * j]) * inv, __uint_as_float(o[2 * j + 1]) * inv, oh[j], ol[j]);
+                        const size_t off = static_cast<size_t>(un.t0 + row) * p.H + un.h * DH + c * 32;
+                        uint4* dh = reinterpret_cast<uint4*>(p.ctx_hi + off);
+                        uint4* dl = reinterpret_cast<uint4*>(p.ctx_lo + off);
+#pragma unroll
+                        for (int q4 = 0; q4 < 4; ++q4) {
+                            dh[q4] = make_uint4(oh[4 * q4], oh[4 * q4 + 1], oh[4 * q4 + 2], oh[4 * q4 + 3]);
+                            dl[q4] = make_uint4(ol[4 * q4], ol[4 * q4 + 1], ol[4 * q4 + 2], ol[4 * q4 + 3]);
+                        }
+                    }
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (warp == 1) tmem_dealloc<512>(tmem_base);
+}

@@ -130,112 +130,13 @@ __global__ void ln_kernel(const float* __restrict__ pre, int T, int H, const flo
     warp_layernorm_store(v, per_lane, H, eps, g, b, hi + static_cast<size_t>(t) * H, lo + static_cast<size_t>(t) * H);
 }
 
-// Self-attention of one (sequence, head): softmax(Q K^T / sqrt(dh)) V over the sequence's own
-// tokens, fp32, streaming softmax over key blocks.  thread = query row.
-template <int DH>
-__global__ void __launch_bounds__(128) attention_kernel(const float* __restrict__ qkv, const int* __restrict__ cu,
-                                                        int H, float scale, __half* __restrict__ ctx_hi,
-                                                        __half* __restrict__ ctx_lo) {
-    constexpr int KB = 64;   // keys per smem block
-    __shared__ __align__(16) float Ks[KB * DH];
-    __shared__ __align__(16) float Vs[KB * DH];
-    const int b = blockIdx.x, h = blockIdx.y;
-    const int t0 = cu[b], S = cu[b + 1] - t0;
-    const int ld = 3 * H;
-    const float* base = qkv + static_cast<size_t>(t0) * ld + h * DH;
-    for (int r0 = 0; r0 < S; r0 += blockDim.x) {
-        const int qi = r0 + threadIdx.x;
-        const bool active = qi < S;
-        float q[DH], acc[DH];
-#pragma unroll
-        for (int d = 0; d < DH; d += 4) {
-            float4 v = active ? *reinterpret_cast<const float4*>(base + static_cast<size_t>(qi) * ld + d) : make_float4(0, 0, 0, 0);
-            q[d] = v.x * scale; q[d + 1] = v.y * scale; q[d + 2] = v.z * scale; q[d + 3] = v.w * scale;
-            acc[d] = acc[d + 1] = acc[d + 2] = acc[d + 3] = 0.f;
-        }
-        float m = -INFINITY, l = 0.f;
-        for (int k0 = 0; k0 < S; k0 += KB) {
-            const int nk = min(KB, S - k0);
-            __syncthreads();
-            for (int e = threadIdx.x; e < nk * (DH / 4); e += blockDim.x) {
-                const int j = e / (DH / 4), d4 = e % (DH / 4);
-                const float* rowp = base + static_cast<size_t>(k0 + j) * ld + d4 * 4;
-                *reinterpret_cast<float4*>(&Ks[j * DH + d4 * 4]) = *reinterpret_cast<const float4*>(rowp + H);
-                *reinterpret_cast<float4*>(&Vs[j * DH + d4 * 4]) = *reinterpret_cast<const float4*>(rowp + 2 * H);
-            }
-            __syncthreads();
-            if (active) {
-                for (int j0 = 0; j0 < nk; j0 += 16) {
-                    float s[16];
-                    float bm = m;
-#pragma unroll
-                    for (int jj = 0; jj < 16; ++jj) {
-                        const int j = j0 + jj;
-                        float a = -INFINITY;
-                        if (j < nk) {
-                            a = 0.f;
-                            const float4* kr = reinterpret_cast<const float4*>(&Ks[j * DH]);
-#pragma unroll
-                            for (int d4 = 0; d4 < DH / 4; ++d4) {
-                                const float4 kv = kr[d4];
-                                a = fmaf(q[d4 * 4], kv.x, a); a = fmaf(q[d4 * 4 + 1], kv.y, a);
-                                a = fmaf(q[d4 * 4 + 2], kv.z, a); a = fmaf(q[d4 * 4 + 3], kv.w, a);
-                            }
-                        }
-                        s[jj] = a;
-                        bm = fmaxf(bm, a);
-                    }
-                    const float corr = expf(m - bm);   // m = -inf on the first block -> 0
-                    l *= corr;
-#pragma unroll
-                    for (int d = 0; d < DH; ++d) acc[d] *= corr;
-                    m = bm;
-#pragma unroll
-                    for (int jj = 0; jj < 16; ++jj) {
-                        const int j = j0 + jj;
-                        if (j < nk) {
-                            const float pj = expf(s[jj] - m);
-                            l += pj;
-                            const float4* vr = reinterpret_cast<const float4*>(&Vs[j * DH]);
-#pragma unroll
-                            for (int d4 = 0; d4 < DH / 4; ++d4) {
-                                const float4 vv = vr[d4];
-                                acc[d4 * 4] = fmaf(pj, vv.x, acc[d4 * 4]); acc[d4 * 4 + 1] = fmaf(pj, vv.y, acc[d4 * 4 + 1]);
-                                acc[d4 * 4 + 2] = fmaf(pj, vv.z, acc[d4 * 4 + 2]); acc[d4 * 4 + 3] = fmaf(pj, vv.w, acc[d4 * 4 + 3]);
-                            }
-                        }
-                    }
-                }
-            }
-        }
-        if (active) {
-            const float inv = 1.0f / l;
-            const size_t o = static_cast<size_t>(t0 + qi) * H + h * DH;
-#pragma unroll
-            for (int d = 0; d < DH; d += 2) {
-                __half h0, l0, h1, l1;
-                split_f16(acc[d] * inv, h0, l0);
-                split_f16(acc[d + 1] * inv, h1, l1);
-                *reinterpret_cast<__half2*>(ctx_hi + o + d) = __halves2half2(h0, h1);
-                *reinterpret_cast<__half2*>(ctx_lo + o + d) = __halves2half2(l0, l1);
-            }
-        }
-    }
-}
-
-// ---------------------------------------------------------------------------------------------------
-// Tensor-core self-attention.  One CTA = (sequence, head, block of 128 query rows); one warp = 16 query
-// rows.  Q K^T and P V run on mma.sync.m16n8k16 (f16 in, f32 accumulate) with the same 3-term hi/lo
-// split as the GEMMs (q, k, p, v are all fp32 values carried as fp16 pairs), so scores and context keep
-// fp32 accuracy.  Keys stream through shared memory in super-blocks of kKeySB (split fp16 planes, K as
-// [key][d], V transposed as [d][key]); softmax is the streaming (running max / sum) form in fp32.
-// ---------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
     asm volatile(
         "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
         : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
         : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
 }
+
 __device__ __forceinline__ void split_pack(float x, float y, uint32_t& hi, uint32_t& lo) {
     __half hx, lx, hy, ly;
     split_f16(x, hx, lx);
@@ -247,184 +148,8 @@ __device__ __forceinline__ void split_pack(float x, float y, uint32_t& hi, uint3
 
 constexpr int kKeySB = 256;   // keys resident in shared memory at a time
 
-template <int DH>
-__global__ void __launch_bounds__(256) attention_mma_kernel(const float* __restrict__ qkv, const int* __restrict__ cu,
-                                                            int H, float scale, __half* __restrict__ ctx_hi,
-                                                            __half* __restrict__ ctx_lo) {
-    constexpr int KSTR = DH + 8;            // halves per K row (bank-conflict-free fragment loads)
-    constexpr int VSTR = kKeySB + 8;        // halves per V^T row
-    constexpr int KS = DH / 16;             // k-steps of Q K^T
-    constexpr int NT = DH / 8;              // n-tiles of the output
-    extern __shared__ __align__(16) unsigned char att_smem[];
-    __half* Kh = reinterpret_cast<__half*>(att_smem);
-    __half* Kl = Kh + kKeySB * KSTR;
-    __half* Vh = Kl + kKeySB * KSTR;        // [DH][VSTR]
-    __half* Vl = Vh + DH * VSTR;
-
-    const int b = blockIdx.x, h = blockIdx.y;
-    const int t0 = cu[b], S = cu[b + 1] - t0;
-    const int rbase = blockIdx.z * 128;
-    if (rbase >= S) return;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-    const int ld = 3 * H;
-    const float* base = qkv + static_cast<size_t>(t0) * ld + h * DH;
-    const int r0 = rbase + warp * 16;
-    const bool warp_live = r0 < S;
-
-    // Q fragments (pre-scaled), rows r0+g and r0+g+8
-    uint32_t qh[KS][4], ql[KS][4];
-    {
-        const int ra = r0 + g, rb = r0 + g + 8;
-#pragma unroll
-        for (int ks = 0; ks < KS; ++ks) {
-            float2 v0 = make_float2(0.f, 0.f), v1 = v0, v2 = v0, v3 = v0;
-            if (warp_live && ra < S) {
-                v0 = *reinterpret_cast<const float2*>(base + static_cast<size_t>(ra) * ld + ks * 16 + 2 * t);
-                v2 = *reinterpret_cast<const float2*>(base + static_cast<size_t>(ra) * ld + ks * 16 + 2 * t + 8);
-            }
-            if (warp_live && rb < S) {
-                v1 = *reinterpret_cast<const float2*>(base + static_cast<size_t>(rb) * ld + ks * 16 + 2 * t);
-                v3 = *reinterpret_cast<const float2*>(base + static_cast<size_t>(rb) * ld + ks * 16 + 2 * t + 8);
-            }
-            split_pack(v0.x * scale, v0.y * scale, qh[ks][0], ql[ks][0]);
-            split_pack(v1.x * scale, v1.y * scale, qh[ks][1], ql[ks][1]);
-            split_pack(v2.x * scale, v2.y * scale, qh[ks][2], ql[ks][2]);
-            split_pack(v3.x * scale, v3.y * scale, qh[ks][3], ql[ks][3]);
-        }
-    }
-    float oacc[NT][4];
-#pragma unroll
-    for (int n = 0; n < NT; ++n) oacc[n][0] = oacc[n][1] = oacc[n][2] = oacc[n][3] = 0.f;
-    float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;   // rows g and g+8
-
-    for (int sb0 = 0; sb0 < S; sb0 += kKeySB) {
-        const int nk = min(kKeySB, S - sb0);
-        const int nk16 = (nk + 15) & ~15;
-        __syncthreads();
-        // K rows and V^T columns of this super-block, fp32 -> split fp16
-        for (int e = threadIdx.x; e < nk16 * (DH / 4); e += blockDim.x) {
-            const int j = e / (DH / 4), d4 = (e % (DH / 4)) * 4;
-            float4 kv = make_float4(0, 0, 0, 0), vv = kv;
-            if (j < nk) {
-                const float* rowp = base + static_cast<size_t>(sb0 + j) * ld + d4;
-                kv = *reinterpret_cast<const float4*>(rowp + H);
-                vv = *reinterpret_cast<const float4*>(rowp + 2 * H);
-            }
-            uint32_t h01, l01, h23, l23;
-            split_pack(kv.x, kv.y, h01, l01);
-            split_pack(kv.z, kv.w, h23, l23);
-            *reinterpret_cast<uint2*>(Kh + j * KSTR + d4) = make_uint2(h01, h23);
-            *reinterpret_cast<uint2*>(Kl + j * KSTR + d4) = make_uint2(l01, l23);
-            __half vh, vl;
-            split_f16(vv.x, vh, vl); Vh[(d4 + 0) * VSTR + j] = vh; Vl[(d4 + 0) * VSTR + j] = vl;
-            split_f16(vv.y, vh, vl); Vh[(d4 + 1) * VSTR + j] = vh; Vl[(d4 + 1) * VSTR + j] = vl;
-            split_f16(vv.z, vh, vl); Vh[(d4 + 2) * VSTR + j] = vh; Vl[(d4 + 2) * VSTR + j] = vl;
-            split_f16(vv.w, vh, vl); Vh[(d4 + 3) * VSTR + j] = vh; Vl[(d4 + 3) * VSTR + j] = vl;
-        }
-        __syncthreads();
-        if (!warp_live) continue;
-        for (int kb0 = 0; kb0 < nk16; kb0 += 32) {
-            // ---- scores of 16 rows x 32 keys
-            float sacc[4][4];
-#pragma unroll
-            for (int n = 0; n < 4; ++n) {
-                sacc[n][0] = sacc[n][1] = sacc[n][2] = sacc[n][3] = 0.f;
-                const int key = kb0 + n * 8 + g;
-                if (kb0 + n * 8 < nk16) {
-#pragma unroll
-                    for (int ks = 0; ks < KS; ++ks) {
-                        uint32_t bh[2], bl[2];
-                        bh[0] = *reinterpret_cast<const uint32_t*>(Kh + key * KSTR + ks * 16 + 2 * t);
-                        bh[1] = *reinterpret_cast<const uint32_t*>(Kh + key * KSTR + ks * 16 + 2 * t + 8);
-                        bl[0] = *reinterpret_cast<const uint32_t*>(Kl + key * KSTR + ks * 16 + 2 * t);
-                        bl[1] = *reinterpret_cast<const uint32_t*>(Kl + key * KSTR + ks * 16 + 2 * t + 8);
-                        mma16816(sacc[n], qh[ks], bh);
-                        mma16816(sacc[n], ql[ks], bh);
-                        mma16816(sacc[n], qh[ks], bl);
-                    }
-                }
-            }
-            // ---- mask keys past the sequence end, running max
-            float bm0 = -INFINITY, bm1 = -INFINITY;
-#pragma unroll
-            for (int n = 0; n < 4; ++n) {
-                const int k0 = kb0 + n * 8 + 2 * t;
-                if (k0 >= nk) { sacc[n][0] = -INFINITY; sacc[n][2] = -INFINITY; }
-                if (k0 + 1 >= nk) { sacc[n][1] = -INFINITY; sacc[n][3] = -INFINITY; }
-                bm0 = fmaxf(bm0, fmaxf(sacc[n][0], sacc[n][1]));
-                bm1 = fmaxf(bm1, fmaxf(sacc[n][2], sacc[n][3]));
-            }
-            bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffffu, bm0, 1));
-            bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffffu, bm0, 2));
-            bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 1));
-            bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 2));
-            const float mn0 = fmaxf(m0, bm0), mn1 = fmaxf(m1, bm1);   // finite: every block holds >= 1 valid key
-            const float c0 = expf(m0 - mn0), c1 = expf(m1 - mn1);
-            m0 = mn0; m1 = mn1;
-            float ps0 = 0.f, ps1 = 0.f;
-#pragma unroll
-            for (int n = 0; n < 4; ++n) {
-                sacc[n][0] = expf(sacc[n][0] - mn0); sacc[n][1] = expf(sacc[n][1] - mn0);
-                sacc[n][2] = expf(sacc[n][2] - mn1); sacc[n][3] = expf(sacc[n][3] - mn1);
-                ps0 += sacc[n][0] + sacc[n][1];
-                ps1 += sacc[n][2] + sacc[n][3];
-            }
-            l0 = l0 * c0 + ps0;      // per-thread partial sums; reduced across the quad at the end
-            l1 = l1 * c1 + ps1;
-#pragma unroll
-            for (int n = 0; n < NT; ++n) { oacc[n][0] *= c0; oacc[n][1] *= c0; oacc[n][2] *= c1; oacc[n][3] *= c1; }
-            // ---- O += P V   (P fragments come straight from the score accumulators)
-#pragma unroll
-            for (int kk = 0; kk < 2; ++kk) {
-                if (kb0 + kk * 16 < nk16) {
-                    uint32_t ph[4], pl[4];
-                    split_pack(sacc[2 * kk][0], sacc[2 * kk][1], ph[0], pl[0]);
-                    split_pack(sacc[2 * kk][2], sacc[2 * kk][3], ph[1], pl[1]);
-                    split_pack(sacc[2 * kk + 1][0], sacc[2 * kk + 1][1], ph[2], pl[2]);
-                    split_pack(sacc[2 * kk + 1][2], sacc[2 * kk + 1][3], ph[3], pl[3]);
-                    const int key = kb0 + kk * 16 + 2 * t;
-#pragma unroll
-                    for (int n = 0; n < NT; ++n) {
-                        const int d = n * 8 + g;
-                        uint32_t vh[2], vl[2];
-                        vh[0] = *reinterpret_cast<const uint32_t*>(Vh + d * VSTR + key);
-                        vh[1] = *reinterpret_cast<const uint32_t*>(Vh + d * VSTR + key + 8);
-                        vl[0] = *reinterpret_cast<const uint32_t*>(Vl + d * VSTR + key);
-                        vl[1] = *reinterpret_cast<const uint32_t*>(Vl + d * VSTR + key + 8);
-                        mma16816(oacc[n], ph, vh);
-                        mma16816(oacc[n], pl, vh);
-                        mma16816(oacc[n], ph, vl);
-                    }
-                }
-            }
-        }
-    }
-    if (!warp_live) return;
-    l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
-    l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
-    l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
-    l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
-    const float i0 = 1.0f / l0, i1 = 1.0f / l1;
-    const int ra = r0 + g, rb = r0 + g + 8;
-#pragma unroll
-    for (int n = 0; n < NT; ++n) {
-        const int col = h * DH + n * 8 + 2 * t;
-        uint32_t hi, lo;
-        if (ra < S) {
-            split_pack(oacc[n][0] * i0, oacc[n][1] * i0, hi, lo);
-            *reinterpret_cast<uint32_t*>(ctx_hi + static_cast<size_t>(t0 + ra) * H + col) = hi;
-            *reinterpret_cast<uint32_t*>(ctx_lo + static_cast<size_t>(t0 + ra) * H + col) = lo;
-        }
-        if (rb < S) {
-            split_pack(oacc[n][2] * i1, oacc[n][3] * i1, hi, lo);
-            *reinterpret_cast<uint32_t*>(ctx_hi + static_cast<size_t>(t0 + rb) * H + col) = hi;
-            *reinterpret_cast<uint32_t*>(ctx_lo + static_cast<size_t>(t0 + rb) * H + col) = lo;
-        }
-    }
-}
-
 // ---------------------------------------------------------------------------------------------------
-// attention_planes_kernel: same algorithm as attention_mma_kernel, but Q (pre-scaled), K and V arrive as
+// attention_planes_kernel (mma.sync; sequences the tcgen05 kernel does not take): Q (pre-scaled), K and V arrive as
 // split fp16 planes [T, 3H] written by the QKV GEMM epilogue, so this kernel does no conversion work:
 // K / V tiles are 16-byte copies into shared memory ([key][d] for both) and the P V operand is fetched
 // with ldmatrix.trans.  One CTA = (sequence, head, block of 16*NW query rows), one warp = 16 rows.
@@ -717,6 +442,8 @@ __global__ void join_planes_kernel(const __half* __restrict__ hi, const __half* 
     if (i < n) out[i] = __half2float(hi[i]) + __half2float(lo[i]);
 }
 
+#include "rmu_attention.cuh"
+
 }  // namespace rmu
 
 using namespace rmu;
@@ -738,7 +465,8 @@ struct rmu_encoder {
     int tok_cap = 0, seq_cap = 0;
     std::vector<void*> act_allocs;
     SplitOperand X, CTX, X1, FF, QKVP;   // QKVP: q (pre-scaled) | k | v as split planes [T, 3H]
-    float *QKV = nullptr, *PRE = nullptr;
+    CUtensorMap att_q_hi{}, att_q_lo{}, att_k_hi{}, att_k_lo{};   // tcgen05 attention: boxes {d_h, 128 rows} / {d_h, 64 rows} of QKVP
+    float* PRE = nullptr;                 // fp32 pre-LayerNorm rows (hidden sizes the fused GEMM+LN kernel does not cover)
     int *d_ids = nullptr, *d_typ = nullptr, *d_cu = nullptr;   // staging for the *_host entry points
     float* d_out = nullptr;
     size_t d_out_elems = 0;
@@ -811,7 +539,14 @@ static int ensure_tokens(rmu_encoder* e, int T, int B) {
     if (rc == RMU_OK) rc = planes(&e->X1, H);
     if (rc == RMU_OK) rc = planes(&e->FF, F);
     if (rc == RMU_OK) rc = planes(&e->QKVP, 3 * H);
-    if (rc == RMU_OK) rc = dev_alloc(e->act_allocs, &e->QKV, static_cast<size_t>(cap) * 3 * H);
+    if (rc == RMU_OK) {
+        const int DH = H / e->cfg.heads;
+        const uint64_t pitch = static_cast<uint64_t>(3) * H * sizeof(__half);
+        rc = make_tmap_2d(&e->att_q_hi, e->QKVP.hi, cap, 3 * H, pitch, DH, kAtcRows, 2);
+        if (rc == RMU_OK) rc = make_tmap_2d(&e->att_q_lo, e->QKVP.lo, cap, 3 * H, pitch, DH, kAtcRows, 2);
+        if (rc == RMU_OK) rc = make_tmap_2d(&e->att_k_hi, e->QKVP.hi, cap, 3 * H, pitch, DH, 64, 2);
+        if (rc == RMU_OK) rc = make_tmap_2d(&e->att_k_lo, e->QKVP.lo, cap, 3 * H, pitch, DH, 64, 2);
+    }
     if (rc == RMU_OK) rc = dev_alloc(e->act_allocs, &e->PRE, static_cast<size_t>(cap) * H);
     if (rc == RMU_OK) rc = dev_alloc(e->act_allocs, &e->d_ids, static_cast<size_t>(cap));
     if (rc == RMU_OK) rc = dev_alloc(e->act_allocs, &e->d_typ, static_cast<size_t>(cap));
@@ -843,23 +578,39 @@ static int run_encoder(rmu_encoder* e, const int32_t* ids, const int32_t* type_i
     const float scale = 1.0f / sqrtf(static_cast<float>(DH));
     for (int l = 0; l < c.layers; ++l) {
         EncLayer& L = e->layers[l];
+        // RMU_ATTN_MODE: 0 = tcgen05 attention where the shape allows it (else the mma.sync kernel), 3 = always mma.sync
         static const int attn_mode = [] { const char* e = getenv("RMU_ATTN_MODE"); return e ? atoi(e) : 0; }();
         GemmParams g{};
         g.M = T; g.N = 3 * H; g.K = H; g.bias = L.bqkv;
-        if (attn_mode == 0) {
-            // q (scaled by 1/sqrt(dh)), k, v leave the GEMM as split fp16 planes: attention does no conversions
-            // (the softmax runs in base 2: q also carries log2(e))
-            g.out_hi = e->QKVP.hi; g.out_lo = e->QKVP.lo; g.qcols = H; g.qscale = scale * 1.4426950408889634f;
-            rc = launch_gemm(GEMM_BIAS_SPLIT_QSCALE, e->X, L.Wqkv, g, e->sms, st);
-        } else {
-            g.out_f32 = e->QKV;
-            rc = launch_gemm(GEMM_BIAS_F32, e->X, L.Wqkv, g, e->sms, st);
-        }
+        // q (scaled by 1/sqrt(dh)), k, v leave the GEMM as split fp16 planes: attention does no conversions
+        // (the softmax runs in base 2: q also carries log2(e))
+        g.out_hi = e->QKVP.hi; g.out_lo = e->QKVP.lo; g.qcols = H; g.qscale = scale * 1.4426950408889634f;
+        rc = launch_gemm(GEMM_BIAS_SPLIT_QSCALE, e->X, L.Wqkv, g, e->sms, st);
         if (rc != RMU_OK) return rc;
-        dim3 ag(static_cast<unsigned>(B), static_cast<unsigned>(c.heads));
         {
             ProfScope _ps(PROF_ATTN, st);
-            if (attn_mode == 0) {
+            // tcgen05 attention: all keys of a sequence in one TMEM score tile (<= 256 - d_h keys) and at least two operand
+            // slots in shared memory; longer sequences take the mma.sync kernel (RMU_ATTN_MODE=3 forces it)
+            const int kp = (max_seqlen + 63) / 64 * 64;
+            const int slot_bytes = 2 * kAtcRows * DH * 2 + 4 * kp * DH * 2;
+            const int nslots = std::min(kAtcMaxSlots, (227 * 1024 - 1024 - kAtcStateBytes) / slot_bytes);
+            if (attn_mode == 0 && max_seqlen <= kAtcBufCols - DH && nslots >= 2) {
+                AtcParams ap{};
+                ap.cu = cu; ap.B = B; ap.heads = c.heads; ap.H = H; ap.row_tiles = (max_seqlen + kAtcRows - 1) / kAtcRows;
+                ap.kp = kp; ap.nslots = nslots; ap.ctx_hi = e->CTX.hi; ap.ctx_lo = e->CTX.lo;
+                ap.nacc = (max_seqlen + 31) / 32 * 32 <= kAtcBufCols - 3 * DH ? 3 : 1;
+                const size_t smem = 1024 + static_cast<size_t>(nslots) * slot_bytes + kAtcStateBytes;
+                const long long nunits = static_cast<long long>(B) * ap.row_tiles * c.heads;
+                const unsigned grid = static_cast<unsigned>(std::min<long long>(e->sms, nunits));
+                if (DH == 32) {
+                    // always the device maximum: concurrent callers (other handles, other sequence lengths) must never lower it
+                    RMU_CUDA(cudaFuncSetAttribute(attention_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+                    attention_tc_kernel<32><<<grid, kAtcThreads, smem, st>>>(e->att_q_hi, e->att_q_lo, e->att_k_hi, e->att_k_lo, ap);
+                } else {
+                    RMU_CUDA(cudaFuncSetAttribute(attention_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+                    attention_tc_kernel<64><<<grid, kAtcThreads, smem, st>>>(e->att_q_hi, e->att_q_lo, e->att_k_hi, e->att_k_lo, ap);
+                }
+            } else {
                 // RMU_ATTN_WARPS = 5: 80-row CTAs, four per SM (same warps/SM, K/V staged twice per 147-token sequence)
                 static const int nw_env = [] { const char* e = getenv("RMU_ATTN_WARPS"); return e ? atoi(e) : kAttWarps; }();
                 const int nw = (nw_env == 5 && DH == 32) ? 5 : kAttWarps;
@@ -871,28 +622,8 @@ static int run_encoder(rmu_encoder* e, const int32_t* ids, const int32_t* type_i
                 const size_t smem = 4 * sizeof(__half) * static_cast<size_t>(ksb) * (DH + 8);
                 auto kern = DH == 32 ? (nw == 5 ? attention_planes_kernel<32, 4, 5> : attention_planes_kernel<32, 2>)
                                      : attention_planes_kernel<64, 1>;   // d_h = 64 needs > 96 registers
-                static bool attr_set[3] = {false, false, false};
-                const int ki = DH == 32 ? (nw == 5 ? 2 : 0) : 1;
-                if (!attr_set[ki]) {
-                    RMU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_max)));
-                    attr_set[ki] = true;
-                }
+                RMU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_max)));
                 kern<<<pg, nw * 32, smem, st>>>(e->QKVP.hi, e->QKVP.lo, cu, H, ksb, e->CTX.hi, e->CTX.lo);
-            } else if (attn_mode == 2) {
-                if (DH == 32) attention_kernel<32><<<ag, 128, 0, st>>>(e->QKV, cu, H, scale, e->CTX.hi, e->CTX.lo);
-                else attention_kernel<64><<<ag, 128, 0, st>>>(e->QKV, cu, H, scale, e->CTX.hi, e->CTX.lo);
-            } else {
-                dim3 mg(static_cast<unsigned>(B), static_cast<unsigned>(c.heads), static_cast<unsigned>((max_seqlen + 127) / 128));
-                const size_t smem = 2 * sizeof(__half) * (static_cast<size_t>(kKeySB) * (DH + 8) + static_cast<size_t>(DH) * (kKeySB + 8));
-                if (DH == 32) {
-                    static bool set32 = false;
-                    if (!set32) { RMU_CUDA(cudaFuncSetAttribute(attention_mma_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem))); set32 = true; }
-                    attention_mma_kernel<32><<<mg, 256, smem, st>>>(e->QKV, cu, H, scale, e->CTX.hi, e->CTX.lo);
-                } else {
-                    static bool set64 = false;
-                    if (!set64) { RMU_CUDA(cudaFuncSetAttribute(attention_mma_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem))); set64 = true; }
-                    attention_mma_kernel<64><<<mg, 256, smem, st>>>(e->QKV, cu, H, scale, e->CTX.hi, e->CTX.lo);
-                }
             }
         }
         count_launch();

@@ -11,18 +11,12 @@ int make_split_operand(SplitOperand* op, __half* hi, __half* lo, int64_t rows, i
     const uint64_t pitch = static_cast<uint64_t>(cols) * sizeof(__half);
     int rc = make_tmap_2d(&op->map_hi, hi, static_cast<uint64_t>(rows), static_cast<uint64_t>(cols), pitch, kGemmBK, 128, 2);
     if (rc == RMU_OK) rc = make_tmap_2d(&op->map_lo, lo, static_cast<uint64_t>(rows), static_cast<uint64_t>(cols), pitch, kGemmBK, 128, 2);
-    op->box64_rows = is_activation ? kWideBM : kWideBN;
-    if (rc == RMU_OK) rc = make_tmap_2d(&op->map64_hi, hi, static_cast<uint64_t>(rows), static_cast<uint64_t>(cols), pitch, 32, op->box64_rows, 2);
-    if (rc == RMU_OK) rc = make_tmap_2d(&op->map64_lo, lo, static_cast<uint64_t>(rows), static_cast<uint64_t>(cols), pitch, 32, op->box64_rows, 2);
-    if (rc == RMU_OK) rc = make_tmap_2d(&op->mapw_hi, hi, static_cast<uint64_t>(rows), static_cast<uint64_t>(cols), pitch, 64, op->box64_rows, 2);
-    if (rc == RMU_OK) rc = make_tmap_2d(&op->mapw_lo, lo, static_cast<uint64_t>(rows), static_cast<uint64_t>(cols), pitch, 64, op->box64_rows, 2);
+    op->is_weight = !is_activation;
     if (!is_activation) {
         if (rc == RMU_OK) rc = make_tmap_2d(&op->map192_hi, hi, static_cast<uint64_t>(rows), static_cast<uint64_t>(cols), pitch, 64, 192, 2);
         if (rc == RMU_OK) rc = make_tmap_2d(&op->map192_lo, lo, static_cast<uint64_t>(rows), static_cast<uint64_t>(cols), pitch, 64, 192, 2);
         if (rc == RMU_OK) rc = make_tmap_2d(&op->map256_hi, hi, static_cast<uint64_t>(rows), static_cast<uint64_t>(cols), pitch, 64, 256, 2);
         if (rc == RMU_OK) rc = make_tmap_2d(&op->map256_lo, lo, static_cast<uint64_t>(rows), static_cast<uint64_t>(cols), pitch, 64, 256, 2);
-        if (rc == RMU_OK) rc = make_tmap_2d(&op->map96_hi, hi, static_cast<uint64_t>(rows), static_cast<uint64_t>(cols), pitch, 64, 96, 2);
-        if (rc == RMU_OK) rc = make_tmap_2d(&op->map96_lo, lo, static_cast<uint64_t>(rows), static_cast<uint64_t>(cols), pitch, 64, 96, 2);
     }
     return rc;
 }
@@ -33,37 +27,11 @@ static int gemm_l2_prefetch() {
     return v;
 }
 
-static int gemm_variant() {
-    static const int v = [] { const char* e = getenv("RMU_GEMM_VARIANT"); return e ? atoi(e) : 0; }();
-    return v;   // 0: 128x128x64 (SW128, 3 stages)   1: 256x128x32 (SW64, 4 stages)   2: 256x128x64 (SW128, 2 stages)
-}
-
-template <int MODE, int BK>
-static int launch_wide(const SplitOperand& A, const SplitOperand& W, const GemmParams& p, int sms, cudaStream_t st) {
-    auto kern = gemm_f16x3_wide_kernel<MODE, BK>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        RMU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kWideSmem)));
-        attr_set = true;
-    }
-    const int tiles = ((p.M + kWideBM - 1) / kWideBM) * (p.N / kWideBN);
-    const int grid = tiles < sms ? tiles : sms;
-    ProfScope _ps(PROF_GEMM, st);
-    if (BK == 32) kern<<<grid, kGemmThreads, kWideSmem, st>>>(A.map64_hi, A.map64_lo, W.map64_hi, W.map64_lo, p);
-    else kern<<<grid, kGemmThreads, kWideSmem, st>>>(A.mapw_hi, A.mapw_lo, W.mapw_hi, W.mapw_lo, p);
-    count_launch();
-    RMU_CHECK_LAUNCH();
-    return RMU_OK;
-}
-
 template <int MODE, int BN>
 static int launch_bn(const SplitOperand& A, const SplitOperand& W, const GemmParams& p, int sms, cudaStream_t st) {
     auto kern = gemm_f16x3_kernel<MODE, BN>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        RMU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kGemmSmem)));
-        attr_set = true;
-    }
+    // the attribute is per device and the call is cheap: set it on every launch (one process may drive several GPUs)
+    RMU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kGemmSmem)));
     const int tiles = ((p.M + kGemmBM - 1) / kGemmBM) * (p.N / BN);
     const int grid = tiles < sms ? tiles : sms;
     ProfScope _ps(PROF_GEMM, st);
@@ -75,34 +43,15 @@ static int launch_bn(const SplitOperand& A, const SplitOperand& W, const GemmPar
     return RMU_OK;
 }
 
-template <int MODE>
-static int launch_pair(const SplitOperand& A, const SplitOperand& W, const GemmParams& p, int sms, cudaStream_t st) {
-    auto kern = gemm_f16x3_pair_kernel<MODE>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        RMU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kPairSmem)));
-        attr_set = true;
-    }
-    const int tiles = ((p.M + 255) / 256) * (p.N / kPairBN);
-    int grid = 2 * std::min(tiles, sms / 2);          // whole CTA pairs
-    ProfScope _ps(PROF_GEMM, st);
-    kern<<<grid, kGemmThreads, kPairSmem, st>>>(A.map_hi, A.map_lo, W.map96_hi, W.map96_lo, p);
-    count_launch();
-    RMU_CHECK_LAUNCH();
-    return RMU_OK;
-}
-
 // tile width: RMU_GEMM_BN = 128 | 192 | 256 forces one (when it divides N); default 192, else 256, else 128
 template <int MODE>
 static int launch_mode(const SplitOperand& A, const SplitOperand& W, const GemmParams& p, int sms, cudaStream_t st) {
-    static const int pair = [] { const char* e = getenv("RMU_GEMM_PAIR"); return e ? atoi(e) : 0; }();
-    if (pair && p.N % kPairBN == 0 && W.box64_rows == kWideBN) return launch_pair<MODE>(A, W, p, sms, st);
     static const int force = [] { const char* e = getenv("RMU_GEMM_BN"); return e ? atoi(e) : 0; }();
     int bn = 128;
     if (force == 128 || force == 192 || force == 256) { if (p.N % force == 0) bn = force; }
     else if (p.N % 192 == 0) bn = 192;      // measured best on the MiniLM / bge shapes (768, 1152, 1536, 2304, 3072 ...)
     else if (p.N % 256 == 0) bn = 256;
-    if (W.box64_rows != kWideBN) bn = 128;   // operand without the wide weight maps
+    if (!W.is_weight) bn = 128;              // operand without the wide weight maps
     if (bn == 256) return launch_bn<MODE, 256>(A, W, p, sms, st);
     if (bn == 192) return launch_bn<MODE, 192>(A, W, p, sms, st);
     return launch_bn<MODE, 128>(A, W, p, sms, st);
@@ -110,7 +59,7 @@ static int launch_mode(const SplitOperand& A, const SplitOperand& W, const GemmP
 
 bool gemm_ln_supported(const SplitOperand& W, int N) {
     static const int off = [] { const char* e = getenv("RMU_LN_FUSED"); return e ? atoi(e) == 0 : 0; }();
-    return !off && W.box64_rows == kWideBN && (N == 2 * kLnBN || N == 4 * kLnBN);
+    return !off && W.is_weight && (N == 2 * kLnBN || N == 4 * kLnBN);
 }
 
 int launch_gemm_ln(const SplitOperand& A, const SplitOperand& W, const GemmLnParams& p_in, int sms, cudaStream_t st) {
@@ -126,12 +75,8 @@ int launch_gemm_ln(const SplitOperand& A, const SplitOperand& W, const GemmLnPar
     // bounds it: 158 -> 145 us at K = 384) and the cluster is a pair (shared-memory budget); RMU_LN_EPI = 8 | 12 forces
     static const int epi_env = [] { const char* e = getenv("RMU_LN_EPI"); return e ? atoi(e) : 0; }();
     const bool epi12 = CL == 2 && (epi_env == 12 || (epi_env == 0 && p.K <= 512));
-    static bool attr_set[2] = {false, false};
-    if (!attr_set[epi12]) {
-        if (epi12) RMU_CUDA(cudaFuncSetAttribute(gemm_f16x3_ln_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(ln_smem_bytes(12))));
-        else RMU_CUDA(cudaFuncSetAttribute(gemm_f16x3_ln_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(ln_smem_bytes(8))));
-        attr_set[epi12] = true;
-    }
+    if (epi12) RMU_CUDA(cudaFuncSetAttribute(gemm_f16x3_ln_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(ln_smem_bytes(12))));
+    else RMU_CUDA(cudaFuncSetAttribute(gemm_f16x3_ln_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(ln_smem_bytes(8))));
     const int m_blks = (p.M + kGemmBM - 1) / kGemmBM;
     const int clusters = std::max(1, std::min(m_blks, sms / CL));
     cudaLaunchConfig_t cfg{};
@@ -161,22 +106,6 @@ int launch_gemm(int mode, const SplitOperand& A, const SplitOperand& W, const Ge
     if (p.N % 128 != 0 || p.K % kGemmBK != 0 || A.cols != p.K || W.cols != p.K || W.rows < p.N || A.rows < p.M) {
         set_error("launch_gemm: shape not supported (N % 128, K % 64)");
         return RMU_ERR_UNSUPPORTED;
-    }
-    if (gemm_variant() == 1 && A.box64_rows == kWideBM && W.box64_rows == kWideBN) {
-        switch (mode) {
-            case GEMM_BIAS_F32: return launch_wide<GEMM_BIAS_F32, 32>(A, W, p, sms, st);
-            case GEMM_BIAS_GELU_SPLIT: return launch_wide<GEMM_BIAS_GELU_SPLIT, 32>(A, W, p, sms, st);
-            case GEMM_BIAS_RESID_F32: return launch_wide<GEMM_BIAS_RESID_F32, 32>(A, W, p, sms, st);
-            case GEMM_BIAS_SPLIT_QSCALE: return launch_wide<GEMM_BIAS_SPLIT_QSCALE, 32>(A, W, p, sms, st);
-        }
-    }
-    if (gemm_variant() == 2 && A.box64_rows == kWideBM && W.box64_rows == kWideBN) {
-        switch (mode) {
-            case GEMM_BIAS_F32: return launch_wide<GEMM_BIAS_F32, 64>(A, W, p, sms, st);
-            case GEMM_BIAS_GELU_SPLIT: return launch_wide<GEMM_BIAS_GELU_SPLIT, 64>(A, W, p, sms, st);
-            case GEMM_BIAS_RESID_F32: return launch_wide<GEMM_BIAS_RESID_F32, 64>(A, W, p, sms, st);
-            case GEMM_BIAS_SPLIT_QSCALE: return launch_wide<GEMM_BIAS_SPLIT_QSCALE, 64>(A, W, p, sms, st);
-        }
     }
     switch (mode) {
         case GEMM_BIAS_F32: return launch_mode<GEMM_BIAS_F32>(A, W, p, sms, st);

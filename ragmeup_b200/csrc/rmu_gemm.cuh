@@ -257,384 +257,6 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tAh, const __grid_constant
 }
 
 
-template <int BK>
-__device__ __forceinline__ uint64_t wide_desc(uint32_t smem_addr) {
-    return BK == 32 ? umma_desc_sw64_kmajor(smem_addr) : umma_desc_sw128_kmajor(smem_addr);
-}
-
-// ---------------------------------------------------------------------------------------------------
-// Wide variant: 256 x 128 output tile per CTA = two M=128 MMAs per K step sharing the W slab, K blocks of
-// 32 (64-byte swizzled rows) so that FOUR 48 KB stages fit: 26 % less L2->SM traffic per MMA cycle and
-// 50 % more latency cover than the 128x128x64 kernel.  Same roles, same epilogues.
-// ---------------------------------------------------------------------------------------------------
-constexpr int kWideBM = 256, kWideBN = 128;
-// BK = 32: rows of 64 B (SWIZZLE_64B), 4 stages of 48 KB.  BK = 64: rows of 128 B (SWIZZLE_128B), 2 stages of 96 KB.
-constexpr size_t kWideSmem = 196608 + kGemmStagingBytes + 256 + 1024;
-
-template <int MODE, int BK>
-__global__ void __launch_bounds__(kGemmThreads, 1)
-gemm_f16x3_wide_kernel(const __grid_constant__ CUtensorMap tAh, const __grid_constant__ CUtensorMap tAl,
-                       const __grid_constant__ CUtensorMap tWh, const __grid_constant__ CUtensorMap tWl,
-                       const GemmParams p) {
-    constexpr uint32_t IDESC = umma_idesc(0 /*f16*/, 128, kWideBN);
-    constexpr int kWideBK = BK;
-    constexpr int kRowBytes = BK * 2;
-    constexpr int kWideStages = BK == 32 ? 4 : 2;
-    constexpr int kWideABytes = 256 * kRowBytes;               // one A plane of a stage
-    constexpr int kWideWBytes = 128 * kRowBytes;               // one W plane of a stage
-    constexpr int kWideStageBytes = 2 * kWideABytes + 2 * kWideWBytes;
-    extern __shared__ uint8_t gemm_smem_raw[];
-    // 1024-byte alignment by OFFSET into the shared array: a pointer round-trip through an integer would lose the
-    // shared address space and turn every staging access into a generic LD/ST
-    uint8_t* smem = gemm_smem_raw + ((1024u - (smem_u32(gemm_smem_raw) & 1023u)) & 1023u);
-    float* staging = reinterpret_cast<float*>(smem + kWideStages * kWideStageBytes);
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + kWideStages * kWideStageBytes + kGemmStagingBytes);
-    uint64_t* empty = full + kWideStages;
-    uint64_t* acc_full = empty + kWideStages;
-    uint64_t* acc_empty = acc_full + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
-
-    const int warp = threadIdx.x >> 5;
-    const unsigned lane = lane_id();
-    if (threadIdx.x == 0) {
-        for (int i = 0; i < kWideStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 32 * kGemmEpiWarps); }
-        fence_mbar_init();
-        prefetch_tmap(&tAh); prefetch_tmap(&tAl); prefetch_tmap(&tWh); prefetch_tmap(&tWl);
-    }
-    if (warp == 1) tmem_alloc<512>(tmem_slot);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-
-    const int m_blks = (p.M + kWideBM - 1) / kWideBM;
-    const int n_blks = p.N / kWideBN;
-    const int k_blks = p.K / kWideBK;
-    const int tiles = m_blks * n_blks;
-
-    if (warp == 0) {
-        if (lane == 0) {
-            int slot = 0;
-            uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-                const int mb = tile / n_blks, nb = tile % n_blks;
-                for (int kb = 0; kb < k_blks; ++kb) {
-                    mbar_wait(&empty[slot], phase ^ 1);
-                    uint8_t* st = smem + slot * kWideStageBytes;
-                    mbar_arrive_expect_tx(&full[slot], kWideStageBytes);
-                    tma_load_2d(st, &tAh, kb * kWideBK, mb * kWideBM, &full[slot], kEvictNormal);
-                    tma_load_2d(st + kWideABytes, &tAl, kb * kWideBK, mb * kWideBM, &full[slot], kEvictNormal);
-                    tma_load_2d(st + 2 * kWideABytes, &tWh, kb * kWideBK, nb * kWideBN, &full[slot], kEvictLast);
-                    tma_load_2d(st + 2 * kWideABytes + kWideWBytes, &tWl, kb * kWideBK, nb * kWideBN, &full[slot], kEvictLast);
-                    if (++slot == kWideStages) { slot = 0; phase ^= 1; }
-                }
-            }
-        }
-    } else if (warp == 1) {
-        if (lane == 0) {
-            int slot = 0;
-            uint32_t phase = 0;
-            int i = 0;
-            for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++i) {
-                const int buf = i & 1;
-                const uint32_t use = static_cast<uint32_t>(i >> 1);
-                mbar_wait(&acc_empty[buf], (use & 1) ^ 1);
-                tc_fence_after();
-                const uint32_t d0 = tmem_base + buf * 256, d1 = d0 + 128;     // rows 0-127 / 128-255 of the tile
-                for (int kb = 0; kb < k_blks; ++kb) {
-                    mbar_wait(&full[slot], phase);
-                    tc_fence_after();
-                    const uint32_t sbase = smem_u32(smem + slot * kWideStageBytes);
-                    const uint64_t dAh0 = wide_desc<BK>(sbase);
-                    const uint64_t dAh1 = wide_desc<BK>(sbase + 128 * kRowBytes);
-                    const uint64_t dAl0 = wide_desc<BK>(sbase + kWideABytes);
-                    const uint64_t dAl1 = wide_desc<BK>(sbase + kWideABytes + 128 * kRowBytes);
-                    const uint64_t dWh = wide_desc<BK>(sbase + 2 * kWideABytes);
-                    const uint64_t dWl = wide_desc<BK>(sbase + 2 * kWideABytes + kWideWBytes);
-#pragma unroll
-                    for (int k = 0; k < kWideBK / 16; ++k) {
-                        const uint64_t off = static_cast<uint64_t>(k * 2);
-                        const uint32_t acc = (kb | k) != 0 ? 1u : 0u;
-                        mma_f16_ss(d0, dAh0 + off, dWh + off, IDESC, acc);
-                        mma_f16_ss(d1, dAh1 + off, dWh + off, IDESC, acc);
-                        mma_f16_ss(d0, dAl0 + off, dWh + off, IDESC, 1u);
-                        mma_f16_ss(d1, dAl1 + off, dWh + off, IDESC, 1u);
-                        mma_f16_ss(d0, dAh0 + off, dWl + off, IDESC, 1u);
-                        mma_f16_ss(d1, dAh1 + off, dWl + off, IDESC, 1u);
-                    }
-                    tc_commit(&empty[slot]);
-                    if (++slot == kWideStages) { slot = 0; phase ^= 1; }
-                }
-                tc_commit(&acc_full[buf]);
-            }
-        }
-    } else {
-        // epilogue warp (2 + ew): TMEM lane quadrant (warp & 3), tile row half (ew >> 2), all four column chunks
-        const int ew = warp - 2;
-        const int quad = warp & 3;
-        const int mh = ew >> 2;
-        float* stg = staging + ew * (32 * kGemmStageRow);
-        const int rsub = static_cast<int>(lane) >> 4, cp = (static_cast<int>(lane) & 15) * 2;
-        int i = 0;
-        for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++i) {
-            const int mb = tile / n_blks, nb = tile % n_blks;
-            const int buf = i & 1;
-            const uint32_t use = static_cast<uint32_t>(i >> 1);
-            mbar_wait(&acc_full[buf], use & 1);
-            tc_fence_after();
-            const int row_base = mb * kWideBM + mh * 128 + quad * 32;
-#pragma unroll 1
-            for (int c = 0; c < 4; ++c) {
-                const int col0 = nb * kWideBN + c * 32;
-                __half2 rsh[16], rsl[16];
-                if (MODE == GEMM_BIAS_RESID_F32) {
-#pragma unroll
-                    for (int q = 0; q < 16; ++q) {
-                        const int grow = row_base + 2 * q + rsub;
-                        if (grow < p.M) {
-                            const size_t o = static_cast<size_t>(grow) * p.N + col0 + cp;
-                            rsh[q] = *reinterpret_cast<const __half2*>(p.res_hi + o);
-                            rsl[q] = *reinterpret_cast<const __half2*>(p.res_lo + o);
-                        }
-                    }
-                }
-                const float2 bia2 = __ldg(reinterpret_cast<const float2*>(p.bias + col0 + cp));
-                uint32_t r[32];
-                tmem_ld32(tmem_addr(tmem_base, quad * 32, buf * 256 + mh * 128 + c * 32), r);
-                tmem_ld_wait();
-                if (c == 3) {
-                    tc_fence_before();
-                    mbar_arrive(&acc_empty[buf]);
-                }
-                const float sc = (MODE == GEMM_BIAS_SPLIT_QSCALE && col0 < p.qcols) ? p.qscale : 1.0f;
-#pragma unroll
-                for (int j = 0; j < 32; ++j) stg[lane * kGemmStageRow + j] = __uint_as_float(r[j]);
-                __syncwarp();
-#pragma unroll
-                for (int rr = 0; rr < 32; rr += 2) {
-                    const int rl = rr + rsub;
-                    const int grow = row_base + rl;
-                    if (grow < p.M) {
-                        // lane = column pair: the bias is a per-lane constant of the chunk
-                        float a = stg[rl * kGemmStageRow + cp] + bia2.x, b = stg[rl * kGemmStageRow + cp + 1] + bia2.y;
-                        if (MODE == GEMM_BIAS_GELU_SPLIT) { a = gelu_erf(a); b = gelu_erf(b); }
-                        if (MODE == GEMM_BIAS_SPLIT_QSCALE) { a *= sc; b *= sc; }
-                        const size_t o = static_cast<size_t>(grow) * p.N + col0 + cp;
-                        if (MODE == GEMM_BIAS_RESID_F32) {
-                            const float2 fh = __half22float2(rsh[rr >> 1]);
-                            const float2 fl = __half22float2(rsl[rr >> 1]);
-                            a += fh.x + fl.x;
-                            b += fh.y + fl.y;
-                        }
-                        if (MODE == GEMM_BIAS_F32 || MODE == GEMM_BIAS_RESID_F32) {
-                            *reinterpret_cast<float2*>(p.out_f32 + o) = make_float2(a, b);
-                        } else {
-                            __half h0, l0, h1, l1;
-                            split_f16(a, h0, l0);
-                            split_f16(b, h1, l1);
-                            *reinterpret_cast<__half2*>(p.out_hi + o) = __halves2half2(h0, h1);
-                            *reinterpret_cast<__half2*>(p.out_lo + o) = __halves2half2(l0, l1);
-                        }
-                    }
-                }
-                __syncwarp();
-            }
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    if (warp == 1) tmem_dealloc<512>(tmem_base);
-}
-
-
-// ---------------------------------------------------------------------------------------------------
-// CTA-pair variant (cta_group::2): a cluster of two CTAs (one SM pair) computes a 256 x 192 tile.  Each
-// CTA stages ITS 128 rows of A and ITS half (96 rows) of the W tile; one thread of the leader CTA issues
-// tcgen05.mma.cta_group::2 (M = 256), which reads both CTAs' shared memory and writes each CTA's own TMEM.
-// Per SM this halves the W bytes pulled from L2 (56 KB per 1152 MMA cycles = 49 B/cycle vs 69-85) and the
-// smem operand reads (73 B/cycle vs 104-128) -- the two limits the single-CTA kernels sit on.
-//   full[s]   (leader only is waited on): 2 arrivals (leader arrive.expect_tx with the bytes of BOTH CTAs,
-//             peer remote arrive) + the TMA bytes of both CTAs (cta_group::2 loads credit the leader).
-//   empty[s], acc_full[b]: per CTA, signalled by the leader's tcgen05.commit multicast to both CTAs.
-//   acc_empty[b] (leader only is waited on): all epilogue threads of both CTAs arrive on the leader's.
-// ---------------------------------------------------------------------------------------------------
-constexpr int kPairBN = 192, kPairStages = 3;
-constexpr int kPairWPlane = (kPairBN / 2) * 128;                          // this CTA's half of one W plane
-constexpr int kPairStageBytes = 2 * kGemmPlaneBytes + 2 * kPairWPlane;    // 56 KB
-constexpr size_t kPairSmem = static_cast<size_t>(kPairStages) * kPairStageBytes + kGemmStagingBytes + 256 + 1024;
-
-template <int MODE>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
-gemm_f16x3_pair_kernel(const __grid_constant__ CUtensorMap tAh, const __grid_constant__ CUtensorMap tAl,
-                       const __grid_constant__ CUtensorMap tWh, const __grid_constant__ CUtensorMap tWl,
-                       const GemmParams p) {
-    constexpr uint32_t IDESC = umma_idesc(0 /*f16*/, 256, kPairBN);
-    extern __shared__ uint8_t gemm_smem_raw[];
-    // 1024-byte alignment by OFFSET into the shared array: a pointer round-trip through an integer would lose the
-    // shared address space and turn every staging access into a generic LD/ST
-    uint8_t* smem = gemm_smem_raw + ((1024u - (smem_u32(gemm_smem_raw) & 1023u)) & 1023u);
-    float* staging = reinterpret_cast<float*>(smem + kPairStages * kPairStageBytes);
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + kPairStages * kPairStageBytes + kGemmStagingBytes);
-    uint64_t* empty = full + kPairStages;
-    uint64_t* acc_full = empty + kPairStages;
-    uint64_t* acc_empty = acc_full + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
-
-    const int warp = threadIdx.x >> 5;
-    const unsigned lane = lane_id();
-    const uint32_t rank = cluster_ctarank();          // 0 = leader
-    if (threadIdx.x == 0) {
-        for (int i = 0; i < kPairStages; ++i) { mbar_init(&full[i], 2); mbar_init(&empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 2 * 32 * kGemmEpiWarps); }
-        fence_mbar_init();
-        prefetch_tmap(&tAh); prefetch_tmap(&tAl); prefetch_tmap(&tWh); prefetch_tmap(&tWl);
-    }
-    cluster_sync_all();                               // barriers of both CTAs exist before anyone signals them
-    if (warp == 1) tmem_alloc_pair<512>(tmem_slot);
-    tc_fence_before();
-    cluster_sync_all();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-
-    const int m_blks = (p.M + 255) / 256;
-    const int n_blks = p.N / kPairBN;
-    const int k_blks = p.K / kGemmBK;
-    const int tiles = m_blks * n_blks;
-    const int cluster_id = blockIdx.x >> 1, nclusters = gridDim.x >> 1;
-
-    if (warp == 0) {
-        if (lane == 0) {
-            int slot = 0;
-            uint32_t phase = 0;
-            for (int tile = cluster_id; tile < tiles; tile += nclusters) {
-                const int mb = tile / n_blks, nb = tile % n_blks;
-                const int mrow = mb * 256 + static_cast<int>(rank) * 128;
-                const int nrow = nb * kPairBN + static_cast<int>(rank) * (kPairBN / 2);
-                for (int kb = 0; kb < k_blks; ++kb) {
-                    mbar_wait(&empty[slot], phase ^ 1);
-                    uint8_t* st = smem + slot * kPairStageBytes;
-                    if (rank == 0) mbar_arrive_expect_tx(&full[slot], 2 * kPairStageBytes);
-                    tma_load_2d_pair(st, &tAh, kb * kGemmBK, mrow, &full[slot], kEvictNormal);
-                    tma_load_2d_pair(st + kGemmPlaneBytes, &tAl, kb * kGemmBK, mrow, &full[slot], kEvictNormal);
-                    tma_load_2d_pair(st + 2 * kGemmPlaneBytes, &tWh, kb * kGemmBK, nrow, &full[slot], kEvictLast);
-                    tma_load_2d_pair(st + 2 * kGemmPlaneBytes + kPairWPlane, &tWl, kb * kGemmBK, nrow, &full[slot], kEvictLast);
-                    if (rank != 0) mbar_arrive_cluster(&full[slot], 0);
-                    if (++slot == kPairStages) { slot = 0; phase ^= 1; }
-                }
-            }
-        }
-    } else if (warp == 1) {
-        if (lane == 0 && rank == 0) {
-            int slot = 0;
-            uint32_t phase = 0;
-            int i = 0;
-            for (int tile = cluster_id; tile < tiles; tile += nclusters, ++i) {
-                const int buf = i & 1;
-                const uint32_t use = static_cast<uint32_t>(i >> 1);
-                mbar_wait(&acc_empty[buf], (use & 1) ^ 1);
-                tc_fence_after();
-                const uint32_t d_addr = tmem_base + buf * kPairBN;
-                for (int kb = 0; kb < k_blks; ++kb) {
-                    mbar_wait(&full[slot], phase);
-                    tc_fence_after();
-                    const uint32_t sbase = smem_u32(smem + slot * kPairStageBytes);
-                    const uint64_t dAh = umma_desc_sw128_kmajor(sbase);
-                    const uint64_t dAl = umma_desc_sw128_kmajor(sbase + kGemmPlaneBytes);
-                    const uint64_t dWh = umma_desc_sw128_kmajor(sbase + 2 * kGemmPlaneBytes);
-                    const uint64_t dWl = umma_desc_sw128_kmajor(sbase + 2 * kGemmPlaneBytes + kPairWPlane);
-#pragma unroll
-                    for (int k = 0; k < kGemmBK / 16; ++k) {
-                        const uint64_t off = static_cast<uint64_t>(k * 2);
-                        mma_f16_ss_pair(d_addr, dAh + off, dWh + off, IDESC, (kb | k) != 0 ? 1u : 0u);
-                        mma_f16_ss_pair(d_addr, dAl + off, dWh + off, IDESC, 1u);
-                        mma_f16_ss_pair(d_addr, dAh + off, dWl + off, IDESC, 1u);
-                    }
-                    tc_commit_pair(&empty[slot]);
-                    if (++slot == kPairStages) { slot = 0; phase ^= 1; }
-                }
-                tc_commit_pair(&acc_full[buf]);
-            }
-        }
-    } else {
-        const int ew = warp - 2;
-        const int quad = warp & 3;
-        const int chalf = ew >> 2;
-        float* stg = staging + ew * (32 * kGemmStageRow);
-        const int rsub = static_cast<int>(lane) >> 4, cp = (static_cast<int>(lane) & 15) * 2;
-        int i = 0;
-        for (int tile = cluster_id; tile < tiles; tile += nclusters, ++i) {
-            const int mb = tile / n_blks, nb = tile % n_blks;
-            const int buf = i & 1;
-            const uint32_t use = static_cast<uint32_t>(i >> 1);
-            mbar_wait(&acc_full[buf], use & 1);
-            tc_fence_after();
-            const int row_base = mb * 256 + static_cast<int>(rank) * 128 + quad * 32;
-#pragma unroll 1
-            for (int cc = 0; cc < kPairBN / 64; ++cc) {
-                const int c = chalf * (kPairBN / 64) + cc;
-                const int col0 = nb * kPairBN + c * 32;
-                __half2 rsh[16], rsl[16];
-                if (MODE == GEMM_BIAS_RESID_F32) {
-#pragma unroll
-                    for (int q = 0; q < 16; ++q) {
-                        const int grow = row_base + 2 * q + rsub;
-                        if (grow < p.M) {
-                            const size_t o = static_cast<size_t>(grow) * p.N + col0 + cp;
-                            rsh[q] = *reinterpret_cast<const __half2*>(p.res_hi + o);
-                            rsl[q] = *reinterpret_cast<const __half2*>(p.res_lo + o);
-                        }
-                    }
-                }
-                const float2 bia2 = __ldg(reinterpret_cast<const float2*>(p.bias + col0 + cp));
-                uint32_t r[32];
-                tmem_ld32(tmem_addr(tmem_base, quad * 32, buf * kPairBN + c * 32), r);
-                tmem_ld_wait();
-                if (cc == kPairBN / 64 - 1) {
-                    tc_fence_before();
-                    mbar_arrive_cluster(&acc_empty[buf], 0);     // the leader's MMA thread owns the hand-back
-                }
-                const float sc = (MODE == GEMM_BIAS_SPLIT_QSCALE && col0 < p.qcols) ? p.qscale : 1.0f;
-#pragma unroll
-                for (int j = 0; j < 32; ++j) stg[lane * kGemmStageRow + j] = __uint_as_float(r[j]);
-                __syncwarp();
-#pragma unroll
-                for (int rr = 0; rr < 32; rr += 2) {
-                    const int rl = rr + rsub;
-                    const int grow = row_base + rl;
-                    if (grow < p.M) {
-                        float a = stg[rl * kGemmStageRow + cp] + bia2.x, b = stg[rl * kGemmStageRow + cp + 1] + bia2.y;
-                        if (MODE == GEMM_BIAS_GELU_SPLIT) { a = gelu_erf(a); b = gelu_erf(b); }
-                        if (MODE == GEMM_BIAS_SPLIT_QSCALE) { a *= sc; b *= sc; }
-                        const size_t o = static_cast<size_t>(grow) * p.N + col0 + cp;
-                        if (MODE == GEMM_BIAS_RESID_F32) {
-                            const float2 fh = __half22float2(rsh[rr >> 1]);
-                            const float2 fl = __half22float2(rsl[rr >> 1]);
-                            a += fh.x + fl.x;
-                            b += fh.y + fl.y;
-                        }
-                        if (MODE == GEMM_BIAS_F32 || MODE == GEMM_BIAS_RESID_F32) {
-                            *reinterpret_cast<float2*>(p.out_f32 + o) = make_float2(a, b);
-                        } else {
-                            __half h0, l0, h1, l1;
-                            split_f16(a, h0, l0);
-                            split_f16(b, h1, l1);
-                            *reinterpret_cast<__half2*>(p.out_hi + o) = __halves2half2(h0, h1);
-                            *reinterpret_cast<__half2*>(p.out_lo + o) = __halves2half2(l0, l1);
-                        }
-                    }
-                }
-                __syncwarp();
-            }
-        }
-    }
-    tc_fence_before();
-    cluster_sync_all();                               // both CTAs are done with TMEM and each other's smem
-    tc_fence_after();
-    if (warp == 1) tmem_dealloc_pair<512>(tmem_base);
-}
-
 // ---------------------------------------------------------------------------------------------------
 // GEMM + bias + residual + LayerNorm -> split planes in ONE kernel (attention-output and FFN-output
 // projections of a post-LN BERT block: transformers BertSelfOutput / BertOutput, modeling_bert.py:287-357).
@@ -940,13 +562,10 @@ struct SplitOperand {
     CUtensorMap map_hi{}, map_lo{};          // box {64 halves, 128 rows}, SWIZZLE_128B  (A side and BN = 128 weights)
     CUtensorMap map192_hi{}, map192_lo{};    // weights only: box {64, 192}
     CUtensorMap map256_hi{}, map256_lo{};    // weights only: box {64, 256}
-    CUtensorMap map96_hi{}, map96_lo{};      // weights only: box {64, 96} (one CTA's half of a 192-wide pair tile)
-    CUtensorMap map64_hi{}, map64_lo{};      // box {32 halves, box64_rows}, SWIZZLE_64B (256x128x32 kernel)
-    CUtensorMap mapw_hi{}, mapw_lo{};        // box {64 halves, box64_rows}, SWIZZLE_128B (256x128x64 kernel)
-    int box64_rows = 0;
+    bool is_weight = false;                  // weights carry the wider boxes
 };
 
-// is_activation: operand is the A side (256-row boxes for the wide kernel) rather than a weight (128-row boxes)
+// is_activation: operand is the A side of the GEMMs (128-row boxes only) rather than a weight
 int make_split_operand(SplitOperand* op, __half* hi, __half* lo, int64_t rows, int cols, bool is_activation);
 // C = A * W^T with the epilogue `mode`; A rows used = p.M (<= A.rows)
 int launch_gemm(int mode, const SplitOperand& A, const SplitOperand& W, const GemmParams& p, int sms, cudaStream_t st);

@@ -243,6 +243,7 @@ struct ExactParams {
     int nq_total;
     unsigned long long* lists; // [nchunks][nq_total][keep]
     int keep;                  // pow2 <= kChunk
+    int nchunks;               // ceil(n / kChunk); the grid strides over them
 };
 
 constexpr int kExactQT = 8;    // queries scored per pass over a chunk of rows
@@ -255,8 +256,9 @@ __global__ void __launch_bounds__(256) exact_scan_kernel(const ExactParams p) {
     float* qs = esm;
     float* sc = esm + kExactQT * p.dim;
     const int nsel = p.nsel ? *p.nsel : p.nq_total;
-    const long long row0 = static_cast<long long>(blockIdx.x) * kChunk;
     const int ngroups = (nsel + kExactQT - 1) / kExactQT;
+    for (int chunk = blockIdx.x; chunk < p.nchunks; chunk += gridDim.x) {
+    const long long row0 = static_cast<long long>(chunk) * kChunk;
     for (int grp = blockIdx.y; grp < ngroups; grp += gridDim.y) {
         const int f0 = grp * kExactQT;
         const int nq = min(kExactQT, nsel - f0);
@@ -293,10 +295,11 @@ __global__ void __launch_bounds__(256) exact_scan_kernel(const ExactParams p) {
                 keys[r] = row < p.n ? make_key(metric_to_rank(sc[i * kChunk + r], p.metric), static_cast<uint32_t>(row)) : 0ull;
             }
             block_bitonic_desc(keys, kChunk);
-            unsigned long long* out = p.lists + (static_cast<long long>(blockIdx.x) * p.nq_total + f0 + i) * p.keep;
+            unsigned long long* out = p.lists + (static_cast<long long>(chunk) * p.nq_total + f0 + i) * p.keep;
             for (int e = threadIdx.x; e < p.keep; e += blockDim.x) out[e] = keys[e];
             __syncthreads();
         }
+    }
     }
 }
 
@@ -647,18 +650,20 @@ struct ScanGeom { int nq, nstages, pair; size_t smem; };
 
 static int env_int(const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; }
 static int scan_kd() { static const int v = env_int("RMU_SCAN_KD", 2) == 1 ? 1 : 2; return v; }          // boxes per stage
-static int scan_pair() { static const int v = env_int("RMU_SCAN_PAIR", 0) != 0 ? 1 : 0; return v; }      // cta_group::2 kernel
+// RMU_SCAN_PAIR: 1 = always the cta_group::2 kernel, 0 = never, unset = when it saves a pass over the corpus
+static int scan_pair_mode() { static const int v = env_int("RMU_SCAN_PAIR", -1); return v; }
 static int scan_stages_cap() { static const int v = env_int("RMU_SCAN_STAGES", 0); return v; }           // study: cap the ring
 static int scan_ablate() { static const int v = env_int("RMU_SCAN_ABLATE", 0); return v; }
 
 template <int NQ, int KD, bool PAIR>
 static int scan_launch_t(const CUtensorMap& tx, const CUtensorMap& tq, const ScanParams& p, int grid, size_t smem, cudaStream_t st) {
     auto kern = scan_rows_kernel<NQ, KD, PAIR>;
-    // per device and cheap: set on every launch (a process may drive several GPUs)
-    RMU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    // per device and cheap: set on every launch (a process may drive several GPUs); always the device maximum, so that
+    // concurrent callers on other handles never lower it under a launch that needs more
+    RMU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(static_cast<unsigned>(grid));
-    cfg.blockDim = dim3(kScanThreads);
+    cfg.blockDim = dim3(64 + 32 * scan_epi_warps(NQ));
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
     cudaLaunchAttribute at[1];
@@ -686,20 +691,24 @@ static int scan_dispatch(const ScanGeom& g, const CUtensorMap& tx, const CUtenso
 }
 
 // largest query block (MMA N) whose resident part fits shared memory at this dimension; 0: dim too large
-static int scan_max_block(int dim) {
+static int scan_block_cap(int dim, bool pair) {
     const int KB = (dim + 31) / 32;
-    const int ncta = scan_pair() ? 2 : 1;
-    int cap = scan_pair() ? kScanMaxQ : 64;
-    while (cap >= 16 && KB * (cap / ncta) * 128 > kScanQOpMax) cap >>= 1;
+    int cap = pair ? kScanMaxQ : 64;
+    while (cap >= 16 && KB * (cap / (pair ? 2 : 1)) * 128 > kScanQOpMax) cap >>= 1;
     return cap >= 16 ? cap : 0;
 }
+static int scan_max_block(int dim) { return std::max(scan_block_cap(dim, false), scan_pair_mode() != 0 ? scan_block_cap(dim, true) : 0); }
 
-// geometry for `rem` queries still to scan
+// geometry for `rem` queries still to scan.  Single CTAs keep the whole query block resident (<= 64 queries at 384
+// dims) and are the faster kernel per pass (measured 10M x 384, Q = 64: 2.26 ms vs 2.36 ms); CTA pairs keep half a
+// block per CTA, so they take twice the queries (or twice the dimension) per pass: 5M x 768, Q = 64: one pass of 2.19 ms
+// instead of two of 2.15 ms; 10M x 384, Q = 128: 3.0 ms instead of 4.5 ms.
 static ScanGeom scan_geometry(int dim, int rem) {
     const int KB = (dim + 31) / 32;
-    const int cap = scan_max_block(dim);
+    const int cap1 = scan_block_cap(dim, false), cap2 = scan_block_cap(dim, true);
     ScanGeom g{};
-    g.pair = scan_pair();
+    g.pair = scan_pair_mode() == 1 || cap1 == 0 || (scan_pair_mode() != 0 && rem > cap1 && cap2 > cap1);
+    const int cap = g.pair ? cap2 : cap1;
     int nq = 16;
     while (nq < cap && nq < rem) nq <<= 1;
     const size_t qop = static_cast<size_t>(KB) * (nq / (g.pair ? 2 : 1)) * 128;
@@ -924,8 +933,10 @@ int rmu_index_search(rmu_index* idx, const float* queries, int nq, int k, int64_
             fp.k = k; fp.id_offset = id_offset; fp.stats_bits = idx->max_norm_bits;
             fp.eps_rel = 2.2e-3f;   // > 2^-9: both TF32 operands truncated to 10 mantissa bits
             fp.out_scores = out_scores; fp.out_ids = reinterpret_cast<long long*>(out_ids); fp.flags = d_flags;
+            const size_t sel_smem = sizeof(unsigned long long) * kSel2Cap + static_cast<size_t>(D) * sizeof(float);
+            RMU_CUDA(cudaFuncSetAttribute(select_rescore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
             { ProfScope _ps(PROF_FINALIZE, st);
-            select_rescore_kernel<<<nql, kSel2Threads, static_cast<size_t>(D) * sizeof(float), st>>>(fp); }
+            select_rescore_kernel<<<nql, kSel2Threads, sel_smem, st>>>(fp); }
             count_launch();
             RMU_CHECK_LAUNCH();
             q0 += nql;
@@ -944,14 +955,15 @@ int rmu_index_search(rmu_index* idx, const float* queries, int nq, int k, int64_
             ExactParams ep{};
             ep.x = idx->x; ep.n = N; ep.dim = D; ep.metric = idx->metric; ep.q = queries;
             ep.qmap = tensor_ok ? d_qmap : nullptr; ep.nsel = tensor_ok ? d_nsel : nullptr; ep.nq_total = nq;
-            ep.lists = d_exact; ep.keep = keepx;
+            ep.lists = d_exact; ep.keep = keepx; ep.nchunks = nchunks;
             const int ngroups = (nq + kExactQT - 1) / kExactQT;
             int gy = tensor_ok ? 1 : std::min(ngroups, std::max(1, (2 * idx->sms + nchunks - 1) / nchunks));
             gy = std::min(gy, 65535);
-            dim3 eg(static_cast<unsigned>(nchunks), static_cast<unsigned>(gy));
+            // behind the tensor scan only flagged queries run here (usually none): a small grid strides over the chunks
+            dim3 eg(static_cast<unsigned>(tensor_ok ? std::min(nchunks, 4 * idx->sms) : nchunks), static_cast<unsigned>(gy));
             const size_t esmem = sizeof(float) * kExactQT * (static_cast<size_t>(D) + kChunk);
             if (esmem > 200 * 1024) { set_error("rmu_index_search: dim too large for the exact scan"); return RMU_ERR_UNSUPPORTED; }
-            RMU_CUDA(cudaFuncSetAttribute(exact_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(esmem)));
+            RMU_CUDA(cudaFuncSetAttribute(exact_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
             { ProfScope _ps(PROF_EXACT, st);
             exact_scan_kernel<<<eg, 256, esmem, st>>>(ep); }
             count_launch();

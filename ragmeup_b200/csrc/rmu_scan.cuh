@@ -19,9 +19,9 @@
 // taking turns).
 //
 // Epilogue: thread = corpus row (TMEM lane), column = query.  Each score is compared with the query's running
-// threshold tau; the few that pass are appended (shared-memory counter, global list) to the (cluster, query)
-// candidate list.  At tile boundaries full lists are sorted by one warp each (warp-shuffle bitonic network) and
-// cut to their best 64; the 64th key becomes the list's floor.
+// threshold tau; the few that pass are appended (shared-memory counter, global list) to the (CTA, query)
+// candidate list.  At tile boundaries lists past 95 entries are sorted by one warp each (warp-shuffle bitonic network)
+// and cut to their best 64; the 64th key becomes the list's floor.
 // Threshold exchange without a second launch: whenever a list is sorted, its 16th best key is published with an
 // atomicMax into gmax[query][cluster % groups].  If every one of `groups` disjoint groups of clusters contains a
 // cluster with >= 16 keys >= v, then >= 16 * groups rows score >= v: tau = min over groups of the group maxima is
@@ -32,12 +32,13 @@
 
 constexpr int kTileRows = 128;                   // corpus rows per CTA tile = TMEM lanes (the pair's MMA has M = 256)
 constexpr int kBoxBytes = kTileRows * 128;       // one TMA box: 128 rows x 32 fp32
-constexpr int kScanThreads = 192;                // warp 0 TMA, warp 1 MMA + TMEM alloc, warps 2..5 epilogue
+constexpr int kScanMaxThreads = 320;             // warp 0 TMA, warp 1 MMA + TMEM alloc, then 4 or 8 epilogue warps
+__host__ __device__ constexpr int scan_epi_warps(int nq) { return nq >= 64 ? 8 : 4; }   // two warps per TMEM lane quadrant split the queries
 constexpr int kAccBufsMax = 8;                   // TMEM accumulators (NQ columns each): min(8, 512 / NQ)
 constexpr int kListCap = 256;                    // slots of a (CTA, query) candidate list
 constexpr int kListKeep = 64;                    // entries a list keeps when it is sorted and cut
-constexpr int kListTrig = 127;                   // a list longer than this at a tile boundary is sorted and cut
-                                                 // (one tile adds <= 128 entries to a list: 127 + 128 < kListCap)
+constexpr int kListTrig = 95;                    // a list longer than this at a tile boundary is sorted and cut
+                                                 // (one tile adds <= 128 entries to a list: 95 + 128 < kListCap)
 constexpr int kPubRank = 16;                     // the published key of a list: its 16th best
 constexpr int kGroupsMax = 16;                   // gmax row length; KSEL <= 16 * kPubRank = 256
 constexpr int kScanStateBytes = 2048;            // mbarriers + per-query state behind the ring
@@ -108,13 +109,16 @@ __device__ __forceinline__ void mma_tf32_ss_pair(uint32_t d_tmem, uint64_t a_des
 //   qbar (leader's): the resident query halves of both CTAs, same scheme as full[].
 // PAIR = false: one CTA, cta_group::1, the whole query block resident.
 template <int NQ, int KD, bool PAIR>
-__global__ void __launch_bounds__(kScanThreads, 1)
+__global__ void __launch_bounds__(64 + 32 * scan_epi_warps(NQ), 1)
 scan_rows_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_q, const ScanParams p) {
     constexpr int NCTA = PAIR ? 2 : 1;
     constexpr int NQH = NQ / NCTA;                       // query rows resident in THIS CTA
     constexpr int STAGE_BYTES = KD * kBoxBytes;
     constexpr int QBLK_BYTES = NQH * 128;                // one K block of this CTA's part of the query operand
     constexpr int CW = NQ < 32 ? NQ : 32;                // accumulator columns per TMEM load
+    constexpr int EPW = scan_epi_warps(NQ);              // epilogue warps: with 8, each TMEM lane quadrant has two, half the queries each
+    constexpr int CPW = NQ / (EPW / 4);                  // query columns one warp looks at
+    constexpr int ETH = 32 * EPW;
     constexpr int NBUF = 512 / NQ < kAccBufsMax ? 512 / NQ : kAccBufsMax;
     constexpr uint32_t IDESC = umma_idesc(2 /*tf32*/, NCTA * kTileRows, NQ);
     static_assert(NQ == 16 || NQ == 32 || NQ == 64 || NQ == 128, "queries per launch");
@@ -146,7 +150,7 @@ scan_rows_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < p.nstages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-        for (int i = 0; i < NBUF; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4 * NCTA); }
+        for (int i = 0; i < NBUF; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], EPW * NCTA); }
         mbar_init(qbar, 1);
         fence_mbar_init();
         prefetch_tmap(&tmap_x);
@@ -235,7 +239,8 @@ scan_rows_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         const int quad = warp & 3;                               // TMEM lane quadrant this warp may touch
         const int er = quad * 32 + static_cast<int>(lane);       // row of the tile
         const int ew = warp - 2;
-        const int et = ew * 32 + static_cast<int>(lane);         // 0..127: per-query duties
+        const int et = ew * 32 + static_cast<int>(lane);         // 0..ETH-1: per-query duties
+        const int c0 = (ew >> 2) * (CPW / CW);                   // first 32-column chunk of this warp
         unsigned long long* mylists = p.lists + static_cast<size_t>(cta) * NQ * kListCap;
         const bool unit_rows = __uint_as_float(__ldg(p.stats_bits + 1)) < 1e-6f;
         const bool has_sc = p.metric == RMU_METRIC_COSINE && !unit_rows;
@@ -246,7 +251,7 @@ scan_rows_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             cnt_s[et] = 0;
             floor_s[et] = -INFINITY;
         }
-        bar_sync_named(1, 128);
+        bar_sync_named(1, ETH);
         bool mine = false;                                       // this thread pushed a list past kListTrig
         int i = 0;
         for (int u = unit; u < nutiles; u += nunits, ++i) {
@@ -260,12 +265,13 @@ scan_rows_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             mbar_wait(&acc_full[buf], use & 1);
             tc_fence_after();
 #pragma unroll
-            for (int c = 0; c < NQ / CW; ++c) {
+            for (int cc = 0; cc < CPW / CW; ++cc) {
+                const int c = c0 + cc;
                 uint32_t r[CW];
                 if constexpr (CW == 32) tmem_ld32(tmem_addr(tmem_base, quad * 32, buf * NQ + c * CW), r);
                 else tmem_ld16(tmem_addr(tmem_base, quad * 32, buf * NQ + c * CW), r);
                 tmem_ld_wait();
-                if (c == NQ / CW - 1) {                          // last TMEM read of this tile: hand the accumulator back
+                if (cc == CPW / CW - 1) {                        // last TMEM read of this tile: hand the accumulator back
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) {                             // the leader's MMA thread owns the hand-back
@@ -274,9 +280,9 @@ scan_rows_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                     }
                 }
                 if (p.ablate & 2) continue;
-                if (p.dbg != nullptr && unit == 0 && i == 0) {
+                if (p.dbg != nullptr && i == 0 && NCTA * unit + rank < 2) {     // tiles 0 and 1 = the first 256 rows
 #pragma unroll
-                    for (int j = 0; j < CW; ++j) p.dbg[(c * CW + j) * 2 * kTileRows + rank * kTileRows + er] = __uint_as_float(r[j]);
+                    for (int j = 0; j < CW; ++j) p.dbg[(c * CW + j) * 2 * kTileRows + (NCTA * unit + rank) * kTileRows + er] = __uint_as_float(r[j]);
                 }
                 float v[CW];
                 unsigned m = 0u;
@@ -306,21 +312,20 @@ scan_rows_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                 }
             }
             if (p.ablate & 2) continue;
-            // ---- tile boundary: sort + cut the lists that need it; after tiles 1, 2, 4, 8, ... every list is
-            // sorted so that fresh keys get published (the thresholds of all CTAs rise together)
-            const bool forced = ((i + 1) & i) == 0 && u + nunits < nutiles;
-            const bool any = bar_red_or_named(1, 128, mine) || forced;
+            // ---- tile boundary: sort + cut the lists that grew past kListTrig (every sort publishes the list's 16th key, so
+            // the thresholds of all CTAs rise together: ~5 sorts per list over a 10M-row scan, most of them in the first tiles)
+            const bool any = bar_red_or_named(1, ETH, mine);
             mine = false;
             if (any) {
-                for (int ql = ew; ql < NQ; ql += 4) {
+                for (int ql = ew; ql < NQ; ql += EPW) {
                     const int n = cnt_s[ql];
-                    if (n > kListTrig || (forced && n >= kPubRank)) {
+                    if (n > kListTrig) {
                         unsigned long long* gslot = p.groups > 0 ? p.gmax + static_cast<size_t>(ql) * kGroupsMax + (cta % p.groups) : nullptr;
                         if (n <= 128) scan_sort_list<4>(mylists + ql * kListCap, n, cnt_s[ql], floor_s[ql], gslot, p.epoch);
                         else scan_sort_list<8>(mylists + ql * kListCap, n, cnt_s[ql], floor_s[ql], gslot, p.epoch);
                     }
                 }
-                bar_sync_named(1, 128);
+                bar_sync_named(1, ETH);
             }
             // ---- refresh this query's threshold from what the other CTAs published
             if (qlive) {
@@ -359,13 +364,14 @@ scan_rows_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
 // sort -> top-k + certificate.  One CTA per query.
 // =====================================================================================================
 constexpr int kSel2Threads = 512;
-constexpr int kSel2Cap = 4096;                   // candidates sorted in shared memory; more -> radix select over the lists
+constexpr int kSel2Cap = 16384;                  // candidates gathered into shared memory (128 KB); more -> radix select over the lists
+constexpr int kSel2Max = 1024;                   // coarse candidates re-scored exactly, at most
 
 struct SelectParams {
     const unsigned long long* lists; const int* counts; const float* floors; const unsigned long long* gmax;
-    int ncl, qb;               // clusters of the scan launch, list blocks per cluster (NQ * CL)
+    int ncl, qb;               // lists per query (CTAs of the scan launch), list blocks per CTA (NQ)
     unsigned epoch; int groups;
-    int ksel;                  // coarse candidates re-scored exactly (<= 1024)
+    int ksel;                  // coarse candidates re-scored exactly (<= kSel2Max)
     const float* x; long long n; int dim; int metric;
     const float* q;            // [launch queries, dim]
     int q0;                    // index of the launch's first query in the outputs
@@ -375,15 +381,51 @@ struct SelectParams {
     float* out_scores; long long* out_ids; int* flags;
 };
 
+// exact_metric with the four fmaf chains of one (query, row) pair spread over the four lanes of a quad (lane & 3 = chain):
+// every chain sees the same elements in the same order and the partial sums are combined as (a0 + a1) + (a2 + a3), so the
+// result is bit-identical to exact_metric.  All four lanes return the value.
+__device__ __forceinline__ float exact_metric_quad(const float* __restrict__ q, const float* __restrict__ x, int D, int metric,
+                                                   float qnorm) {
+    const int c = static_cast<int>(lane_id() & 3u);
+    const int D4 = D & ~3;
+    float a = 0.f, nn = 0.f;
+    if (metric == RMU_METRIC_L2) {
+        for (int d = c; d < D4; d += 4) { const float e = q[d] - x[d]; a = fmaf(e, e, a); }
+        if (c == 0) for (int d = D4; d < D; ++d) { const float e = q[d] - x[d]; a = fmaf(e, e, a); }
+    } else {
+        for (int d = c; d < D4; d += 4) {
+            const float xv = x[d];
+            a = fmaf(q[d], xv, a);
+            if (metric == RMU_METRIC_COSINE) nn = fmaf(xv, xv, nn);
+        }
+        if (c == 0) for (int d = D4; d < D; ++d) {
+            a = fmaf(q[d], x[d], a);
+            if (metric == RMU_METRIC_COSINE) nn = fmaf(x[d], x[d], nn);
+        }
+    }
+    const unsigned qb = lane_id() & ~3u;
+    const float a0 = __shfl_sync(0xffffffffu, a, qb), a1 = __shfl_sync(0xffffffffu, a, qb + 1);
+    const float a2 = __shfl_sync(0xffffffffu, a, qb + 2), a3 = __shfl_sync(0xffffffffu, a, qb + 3);
+    const float s = (a0 + a1) + (a2 + a3);
+    if (metric != RMU_METRIC_COSINE) return s;
+    const float n0 = __shfl_sync(0xffffffffu, nn, qb), n1 = __shfl_sync(0xffffffffu, nn, qb + 1);
+    const float n2 = __shfl_sync(0xffffffffu, nn, qb + 2), n3 = __shfl_sync(0xffffffffu, nn, qb + 3);
+    const float xn = sqrtf((n0 + n1) + (n2 + n3));
+    const float den = qnorm * xn;
+    return den > 0.f ? s / den : 0.f;
+}
+
 __global__ void __launch_bounds__(kSel2Threads) select_rescore_kernel(const SelectParams p) {
-    __shared__ unsigned long long cand[kSel2Cap];
+    __shared__ unsigned long long sel[kSel2Max];
     __shared__ int hist[256];
     __shared__ float red[32];
-    __shared__ int s_n;
+    __shared__ int s_n, s_nsel;
     __shared__ unsigned long long s_prefix;
     __shared__ int s_remaining, s_ties;
     __shared__ float s_tau;
-    extern __shared__ float qs[];                // [dim]
+    extern __shared__ unsigned long long sel_dyn[];  // cand [kSel2Cap], then the query [dim] floats
+    unsigned long long* cand = sel_dyn;
+    float* qs = reinterpret_cast<float*>(sel_dyn + kSel2Cap);
 
     const int f = blockIdx.x;
     const int tid = threadIdx.x;
@@ -413,6 +455,7 @@ __global__ void __launch_bounds__(kSel2Threads) select_rescore_kernel(const Sele
         }
         s_tau = tg;
         s_n = 0;
+        s_nsel = 0;
     }
     float fl = -INFINITY;
     for (int c = tid; c < p.ncl; c += blockDim.x) fl = fmaxf(fl, p.floors[c * p.qb + f]);
@@ -423,15 +466,17 @@ __global__ void __launch_bounds__(kSel2Threads) select_rescore_kernel(const Sele
     fl = red[0];
     for (int w = 1; w < kSel2Threads / 32; ++w) fl = fmaxf(fl, red[w]);
     const float tau = s_tau;
-    const float rejected = fmaxf(tau, fl);       // every row that is in no list scores <= this
+    float bound = fmaxf(tau, fl);                // coarse upper bound of every row that is in no list
     __syncthreads();
 
-    // ---- gather the entries above tau
-    for (int c = warp; c < p.ncl; c += kSel2Threads / 32) {
-        const int n = p.counts[c * p.qb + f];
-        const unsigned long long* b = p.lists + static_cast<size_t>(c * p.qb + f) * kListCap;
-        for (int e = lane; e < n; e += 32) {
-            const unsigned long long key = b[e];
+    // ---- gather the entries above tau (two lists per warp step: the count loads of both are in flight together)
+    for (int c = 2 * warp; c < p.ncl; c += 2 * (kSel2Threads / 32)) {
+        const int n0 = p.counts[c * p.qb + f];
+        const int n1 = c + 1 < p.ncl ? p.counts[(c + 1) * p.qb + f] : 0;
+        const unsigned long long* b0 = p.lists + static_cast<size_t>(c * p.qb + f) * kListCap;
+        const unsigned long long* b1 = b0 + static_cast<size_t>(p.qb) * kListCap;
+        for (int e = lane; e < n0 + n1; e += 32) {
+            const unsigned long long key = e < n0 ? b0[e] : b1[e - n0];
             if (key_score(key) > tau) {
                 const int pos = atomicAdd(&s_n, 1);
                 if (pos < kSel2Cap) cand[pos] = key;
@@ -439,55 +484,57 @@ __global__ void __launch_bounds__(kSel2Threads) select_rescore_kernel(const Sele
         }
     }
     __syncthreads();
-    int n = s_n;
-    float bound = rejected;                      // coarse upper bound of every row outside the candidate set
+    const int n = s_n;
     int ncand;
-    if (n <= kSel2Cap) {
-        int n2 = 32;
-        while (n2 < n) n2 <<= 1;
-        for (int i = n + tid; i < n2; i += blockDim.x) cand[i] = 0ull;
-        block_bitonic_desc(cand, n2);
-        ncand = min(n, p.ksel);
-        if (n > p.ksel) bound = fmaxf(bound, key_score(cand[p.ksel]));
+    if (n <= p.ksel) {                           // every survivor is re-scored
+        for (int i = tid; i < n; i += blockDim.x) sel[i] = cand[i];
+        ncand = n;
     } else {
-        // more survivors than fit: radix-select the ksel-th best key over the lists, then collect
-        const long long total = static_cast<long long>(p.ncl) * kListCap;
-        auto load_key = [&](long long idx) -> unsigned long long {
-            const int c = static_cast<int>(idx / kListCap), e = static_cast<int>(idx % kListCap);
-            if (e >= p.counts[c * p.qb + f]) return 0ull;
-            const unsigned long long key = p.lists[static_cast<size_t>(c * p.qb + f) * kListCap + e];
-            return key_score(key) > tau ? key : 0ull;
-        };
-        const unsigned long long T = block_radix_select(load_key, total, p.ksel, hist, &s_prefix, &s_remaining, &s_ties);
-        __syncthreads();
-        if (tid == 0) s_n = 0;
-        __syncthreads();
-        for (long long idx = tid; idx < total; idx += blockDim.x) {
-            const unsigned long long key = load_key(idx);
-            if (key != 0ull && key >= T) {
-                const int pos = atomicAdd(&s_n, 1);
-                if (pos < kSel2Cap) cand[pos] = key;
+        // the ksel-th best key by radix select (shared memory when the survivors fit, else over the lists), then collect
+        unsigned long long T;
+        if (n <= kSel2Cap) {
+            auto load_key = [&](long long idx) -> unsigned long long { return cand[idx]; };
+            T = block_radix_select(load_key, n, p.ksel, hist, &s_prefix, &s_remaining, &s_ties);
+            __syncthreads();
+            for (int i = tid; i < n; i += blockDim.x) {
+                const unsigned long long key = cand[i];
+                if (key >= T) { const int pos = atomicAdd(&s_nsel, 1); if (pos < kSel2Max) sel[pos] = key; }
+            }
+        } else {
+            const long long total = static_cast<long long>(p.ncl) * kListCap;
+            auto load_key = [&](long long idx) -> unsigned long long {
+                const int c = static_cast<int>(idx / kListCap), e = static_cast<int>(idx % kListCap);
+                if (e >= p.counts[c * p.qb + f]) return 0ull;
+                const unsigned long long key = p.lists[static_cast<size_t>(c * p.qb + f) * kListCap + e];
+                return key_score(key) > tau ? key : 0ull;
+            };
+            T = block_radix_select(load_key, total, p.ksel, hist, &s_prefix, &s_remaining, &s_ties);
+            __syncthreads();
+            for (long long idx = tid; idx < total; idx += blockDim.x) {
+                const unsigned long long key = load_key(idx);
+                if (key != 0ull && key >= T) { const int pos = atomicAdd(&s_nsel, 1); if (pos < kSel2Max) sel[pos] = key; }
             }
         }
         __syncthreads();
-        ncand = min(s_n, p.ksel);
-        bound = fmaxf(bound, key_score(T));      // excluded list entries are below T
-        for (int i = ncand + tid; i < 1024; i += blockDim.x) cand[i] = 0ull;
-        __syncthreads();
-        n = ncand;
+        ncand = min(s_nsel, p.ksel);
+        bound = fmaxf(bound, key_score(T));      // list entries that were not selected are below T
     }
+    __syncthreads();
 
-    // ---- exact re-score (the same arithmetic as the exact scan: bit-identical scores)
-    for (int c = tid; c < ncand; c += blockDim.x) {
-        const uint32_t row = key_row(cand[c]);
-        const float v = exact_metric(qs, p.x + static_cast<long long>(row) * p.dim, p.dim, p.metric, qnorm);
-        cand[c] = make_key(metric_to_rank(v, p.metric), row);
+    // ---- exact re-score, a quad of lanes per candidate (the same arithmetic as the exact scan: bit-identical scores)
+    for (int c0 = 0; c0 < ncand; c0 += kSel2Threads / 4) {
+        const int c = c0 + (tid >> 2);
+        const bool live = c < ncand;
+        const uint32_t row = live ? key_row(sel[c]) : 0u;
+        const float v = exact_metric_quad(qs, p.x + static_cast<long long>(row) * p.dim, p.dim, p.metric, qnorm);
+        __syncwarp();
+        if (live && (tid & 3) == 0) sel[c] = make_key(metric_to_rank(v, p.metric), row);
     }
     int m2 = 32;
     while (m2 < ncand) m2 <<= 1;
     __syncthreads();
-    for (int i = ncand + tid; i < m2; i += blockDim.x) cand[i] = 0ull;
-    block_bitonic_desc(cand, m2);
+    for (int i = ncand + tid; i < m2; i += blockDim.x) sel[i] = 0ull;
+    block_bitonic_desc(sel, m2);
 
     // ---- outputs
     const int qg = p.q0 + f;
@@ -496,9 +543,9 @@ __global__ void __launch_bounds__(kSel2Threads) select_rescore_kernel(const Sele
         float s = missing;
         long long id = -1;
         if (j < ncand) {
-            const float rk = key_score(cand[j]);
+            const float rk = key_score(sel[j]);
             s = p.metric == RMU_METRIC_L2 ? -rk : rk;
-            id = p.id_offset + key_row(cand[j]);
+            id = p.id_offset + key_row(sel[j]);
         }
         p.out_scores[static_cast<long long>(qg) * p.k + j] = s;
         p.out_ids[static_cast<long long>(qg) * p.k + j] = id;
@@ -510,7 +557,7 @@ __global__ void __launch_bounds__(kSel2Threads) select_rescore_kernel(const Sele
         if (bound > -INFINITY) {
             if (ncand < p.k) flag = 1;
             else {
-                const float rk = key_score(cand[p.k - 1]);   // rank value of the k-th exact result
+                const float rk = key_score(sel[p.k - 1]);    // rank value of the k-th exact result
                 const float xmax = __uint_as_float(p.stats_bits[0]);
                 const bool unit = __uint_as_float(p.stats_bits[1]) < 1e-6f && p.metric != RMU_METRIC_IP;
                 float kth_key, scale;                        // in the units of the coarse key

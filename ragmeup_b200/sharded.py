@@ -26,6 +26,8 @@ class ShardedFlatIndex:
             merge_fn = topk_merge
         self.merge_fn = merge_fn
         self._xkey, self._x = None, None
+        self._batches = []          # sizes of the batches passed to add(), in order (identical on every rank)
+        self._preloaded = len(local_index)   # rows that were in the shard before the first add()
         self.offset = 0
         self.total = len(local_index)
         self._sizes = [len(local_index)]
@@ -44,6 +46,46 @@ class ShardedFlatIndex:
         self._sizes = [int(s.item()) for s in sizes]
         self.offset = sum(self._sizes[: self.rank])
         self.total = sum(self._sizes)
+
+    # ------------------------------------------------------------------ sharded ingest (server/RAGHelper.py:423-434)
+    def add(self, vectors) -> Tuple[int, int]:
+        """The reference's ingest loop hands batches of 1000 documents to ``db.add_documents``; here EVERY rank is given
+        the same batch [n, D] and keeps its block of it: rows [r*n//R, (r+1)*n//R).  Offsets are re-synchronised, so
+        searches see the new rows at once.  Returns the (lo, hi) row range of the batch this rank kept."""
+        n = int(vectors.shape[0])
+        lo, hi = self.rank * n // self.world, (self.rank + 1) * n // self.world
+        if hi > lo:
+            self.index.add(vectors[lo:hi])
+        self._batches.append(n)
+        self._sizes = [s + ((r + 1) * n // self.world - r * n // self.world) for r, s in enumerate(self._sizes)] \
+            if len(self._sizes) == self.world else None
+        if self._sizes is None:
+            self.sync_offsets()
+        else:                                   # every rank can compute every shard size: no collective needed
+            self.offset = sum(self._sizes[: self.rank])
+            self.total = sum(self._sizes)
+        return lo, hi
+
+    def to_insertion_order(self, ids):
+        """merged global ids (shard offset + local row) -> position of the row in the order the batches were added
+        (what an unsharded store would have called it); -1 stays -1.  Only for shards filled through :meth:`add`."""
+        import numpy as np
+        if self._preloaded:
+            raise ValueError("to_insertion_order needs shards that were filled through add() only")
+        g = np.asarray(ids.cpu() if hasattr(ids, "cpu") else ids, dtype=np.int64)
+        R = self.world
+        sizes = np.array([[(r + 1) * n // R - r * n // R for n in self._batches] for r in range(R)], dtype=np.int64)   # [R, nb]
+        local_start = np.concatenate([np.zeros((R, 1), np.int64), np.cumsum(sizes, 1)], 1)                             # [R, nb + 1]
+        offsets = np.concatenate([[0], np.cumsum(local_start[:, -1])])                                                 # [R + 1]
+        batch_start = np.concatenate([[0], np.cumsum(self._batches)])
+        out = np.full(g.shape, -1, np.int64)
+        ok = g >= 0
+        r = np.searchsorted(offsets, g[ok], side="right") - 1
+        local = g[ok] - offsets[r]
+        b = np.array([np.searchsorted(local_start[ri], li, side="right") - 1 for ri, li in zip(r, local)], dtype=np.int64)
+        first_kept = np.array([ri * self._batches[bi] // R for ri, bi in zip(r, b)], dtype=np.int64)
+        out[ok] = batch_start[b] + first_kept + (local - local_start[r, b])
+        return out
 
     def _exchange_buffers(self, Q: int, k: int, device):
         """One send record per rank: {scores fp32 [Q, k] | pad to 16 B | ids int64 [Q, k]} as raw bytes; the receive

@@ -18,6 +18,9 @@ class OracleShard:
     def __len__(self):
         return self.x.shape[0]
 
+    def add(self, v):
+        self.x = np.concatenate([self.x, np.asarray(v, np.float32)])
+
     def search(self, q, k, id_offset=0):
         from oracle import flat_ref
         s, i = flat_ref.flat_search(q.numpy(), self.x, k, self.metric, id_offset=id_offset)
@@ -53,6 +56,46 @@ def _worker(rank, world, port, metric, out):
         out[rank] = ok
     finally:
         dist.destroy_process_group()
+
+
+def _ingest_worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle import flat_ref
+        from ragmeup_b200.sharded import ShardedFlatIndex
+        rng = np.random.default_rng(11)
+        batches = [rng.standard_normal((n, 24)).astype(np.float32) for n in (7, 10, 1, 5, 1000)]   # the reference adds 1000 at a time
+        sh = ShardedFlatIndex(OracleShard(np.zeros((0, 24), np.float32), "ip"), merge_fn=oracle_merge)
+        sh.sync_offsets()
+        kept = 0
+        for b in batches:
+            lo, hi = sh.add(b)
+            kept += hi - lo
+        x = np.concatenate(batches)
+        q = rng.standard_normal((5, 24)).astype(np.float32)
+        assert len(sh.index) == kept and sh.total == len(x)
+        s, i = sh.search(torch.from_numpy(q), 9)
+        fs, fi = flat_ref.flat_search(q, x, 9, "ip")
+        got = sh.to_insertion_order(i)
+        out[rank] = bool((got == fi).all()) and bool(np.allclose(s.numpy(), fs, atol=1e-6))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_ingest_block_partition_gloo():
+    """ShardedFlatIndex.add: every rank keeps its block of every batch, offsets stay in sync without a collective,
+    and merged ids map back to the order the documents were added in (server/RAGHelper.py:423-434 is the loop)"""
+    world = 2
+    import socket
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    with mp.Manager() as m:
+        out = m.dict()
+        mp.spawn(_ingest_worker, args=(world, port, out), nprocs=world, join=True)
+        assert dict(out) == {0: True, 1: True}
 
 
 @pytest.mark.parametrize("metric", ["l2", "ip"])

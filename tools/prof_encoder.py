@@ -19,3 +19,10 @@ e0.record()
 for _ in range(IT): enc.classify_tokens(ids, typ, cu, S)
 e1.record(); torch.cuda.synchronize()
 print(f"classify B={B} S={S}: {e0.elapsed_time(e1)/IT:.3f} ms/iter", flush=True)
+if os.environ.get("PROF_CLASSES") == "1":
+    from ragmeup_b200 import _lib
+    _lib.profile_enable(True); _lib.profile_reset()
+    for _ in range(IT): enc.classify_tokens(ids, typ, cu, S)
+    torch.cuda.synchronize()
+    print({k: (round(v[0] / IT, 4), v[1] // IT) for k, v in _lib.profile_read().items() if v[1]}, flush=True)
+    _lib.profile_enable(False)
