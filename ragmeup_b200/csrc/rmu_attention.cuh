@@ -27,15 +27,15 @@
 // TMEM buffer (P V of unit i done), P V of unit i only for its softmax; issued by one thread in program order, each P V
 // sat behind the other group's read-out and the two groups ran in lockstep (measured: 390 us per layer call, the same
 // as the mma.sync kernel, with 38 % of all warp samples waiting for O).
-//   warp 0: TMA producer   warp 1: S issuer + TMEM allocator   warp 2: P V issuer   warps 3-6: softmax group 0   warps 7-10: group 1
+//   warp 0: TMA producer   warp 1: S issuer + TMEM allocator   warp 2: P V issuer   warps 3-10: softmax group 0   warps 11-18: group 1
 #pragma once
 
-constexpr int kAtcThreads = 352;
+constexpr int kAtcThreads = 608;             // 3 control warps + 2 in-flight units x 8 softmax warps
 constexpr int kAtcRows = 128;                 // query rows per unit = MMA M
 constexpr int kAtcBufCols = 256;              // TMEM columns per in-flight unit: S / P from 0, O in the last d_h columns
 constexpr int kAtcMaxSlots = 3;
 constexpr int kAtcMaxChunks = 8;             // 32-key chunks of a score tile (<= 256 keys)
-constexpr int kAtcStateBytes = 512;          // mbarriers behind the operand slots
+constexpr int kAtcStateBytes = 512 + 4 * 128 * 4;   // mbarriers + the row max / row sum exchange of the softmax warps
 
 struct AtcParams {
     const int* cu;          // [B + 1] token offsets
@@ -119,6 +119,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tq_hi, const __grid_cons
     // time).  So each product term (P_hi V_hi, P_lo V_hi, P_hi V_lo) gets its own accumulator when the columns allow it:
     // three independent chains interleave in the pipe, and the read-out adds them up.
     const int OCOL = kAtcBufCols - p.nacc * DH;
+    const int OCOL_C = OCOL;
     // O = P V: A from TMEM (K-major), B = V as it lies in shared memory ([key][d_h]): MN-major -> bit 16
     constexpr uint32_t IDESC_O = umma_idesc(0 /*f16*/, kAtcRows, DH) | (1u << 16);
 
@@ -135,6 +136,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tq_hi, const __grid_cons
     uint64_t* o_full = p_full + 2 * kAtcMaxChunks;         // [2] O of buffer g is complete
     uint64_t* s_free = o_full + 2;                         // [2] the P V MMAs that read buffer g have completed
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_free + 2);
+    float* xch = reinterpret_cast<float*>(state + 512);    // [2 groups][2 halves][128 rows]
 
     const int warp = threadIdx.x >> 5;
     const unsigned lane = lane_id();
@@ -212,11 +214,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tq_hi, const __grid_cons
         // =========================== O = P V issuer ===========================
         if (lane == 0) {
             int i = 0;
+            uint32_t ppar[2] = {0u, 0u};                         // bit c = parity the next wait on p_full[g][c] uses
             for (int u = blockIdx.x; u < nunits; u += gridDim.x) {
                 AtcUnit un;
                 if (!atc_unit(p, u, un)) continue;
                 const int g = i & 1;
-                const uint32_t use = static_cast<uint32_t>(i >> 1);
                 const int slot = i % p.nslots;
                 const uint8_t* sb = smem + slot * slot_bytes;
                 const uint32_t vh = smem_u32(sb + 2 * QBYTES + 2 * kbytes), vl = vh + kbytes;
@@ -228,7 +230,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tq_hi, const __grid_cons
                 // P arrives 32 keys at a time (the same warps read O of the unit two back out before they wrote any of it):
                 // the MMAs of a chunk are issued while the softmax warps are still working on the next one
                 for (int c = 0; c < nchunk; ++c) {
-                    mbar_wait(&p_full[g * kAtcMaxChunks + c], use & 1);
+                    mbar_wait(&p_full[g * kAtcMaxChunks + c], (ppar[g] >> c) & 1u);   // per-barrier parity: sequences differ in chunks
+                    ppar[g] ^= 1u << c;
                     tc_fence_after();
                     for (int j16 = 2 * c; j16 < min(2 * c + 2, nk16); ++j16) {
                         const uint32_t a_hi = pbase + 32 * c + 8 * (j16 & 1), a_lo = a_hi + 16;
@@ -246,11 +249,18 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tq_hi, const __grid_cons
             }
         }
     } else {
-        // =========================== softmax + output: thread = query row ===========================
-        const int grp = (warp - 3) >> 2;                         // which of the two in-flight units this warp serves
+        // =========================== softmax + output: thread = query row, two warps per row ===========================
+        // Each in-flight unit has EIGHT warps: the two warps of a TMEM lane quadrant own the same 32 rows and split the
+        // 32-key chunks (even / odd); row maxima and row sums are exchanged through shared memory.  With one warp per
+        // quadrant a unit's softmax was a 5-chunk serial chain of tcgen05.ld -> exp2 / split -> tcgen05.st -> barrier
+        // latencies (~9900 cycles from S ready to O stored, measured) and two units in flight could not hide it.
+        const int grp = (warp - 3) >> 3;                         // which of the two in-flight units this warp serves
+        const int half = ((warp - 3) >> 2) & 1;                  // which chunks (c & 1) and which half of O's columns
         const int quad = warp & 3;                               // TMEM lane quadrant this warp may touch
         const int r = quad * 32 + static_cast<int>(lane);        // row of the unit
-        const int gtid = (warp - 3 - 4 * grp) * 32 + static_cast<int>(lane);   // thread index inside the group
+        const int htid = ((warp - 3) & 3) * 32 + static_cast<int>(lane);       // thread index inside the (group, half)
+        float* xm = xch + (grp * 2 + half) * kAtcRows;           // my partial row maxima, then my partial row sums
+        const float* xo = xch + (grp * 2 + (half ^ 1)) * kAtcRows;   // the other warp's
         int i = 0;
         for (int u = blockIdx.x; u < nunits; u += gridDim.x) {
             AtcUnit un;
@@ -264,10 +274,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tq_hi, const __grid_cons
             const bool warp_live = un.rt * kAtcRows + quad * 32 < S;      // any row of this warp inside the sequence
             mbar_wait(&s_full[grp], use & 1);
             tc_fence_after();
-            float l = 0.f, m = -INFINITY;
+            // ---- pass 1: row maximum over my chunks, then over both warps of the row
+            float m = -INFINITY;
             if (warp_live) {
-                // ---- pass 1: row maximum
-                for (int c = 0; c < nchunk; ++c) {
+                for (int c = half; c < nchunk; c += 2) {
                     uint32_t s[32];
                     tmem_ld32(tb + c * 32, s);
                     tmem_ld_wait();
@@ -280,9 +290,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tq_hi, const __grid_cons
                     }
                 }
             }
+            xm[r] = m;
+            bar_sync_named(1 + grp, 256);
+            m = fmaxf(m, xo[r]);
+            bar_sync_named(1 + grp, 256);                        // both warps have read the maxima: the slots may take the sums
             // ---- pass 2: P = exp2(S - m) (scores are pre-scaled by log2 e), split, packed back in place; every chunk is
-            // handed to the P V issuer as soon as all four warps of the group have written it
-            for (int c = 0; c < nchunk; ++c) {
+            // handed to the P V issuer as soon as the four warps that own it have written it
+            float l = 0.f;
+            for (int c = half; c < nchunk; c += 2) {
                 if (warp_live) {
                     uint32_t s[32];
                     tmem_ld32(tb + c * 32, s);
@@ -304,45 +319,48 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tq_hi, const __grid_cons
                     tmem_st_wait();
                 }
                 tc_fence_before();
-                bar_sync_named(1 + grp, 128);
-                if (gtid == 0) mbar_arrive(&p_full[grp * kAtcMaxChunks + c]);
+                bar_sync_named(3 + grp * 2 + half, 128);
+                if (htid == 0) mbar_arrive(&p_full[grp * kAtcMaxChunks + c]);
             }
-            // ---- O / l -> split planes
+            xm[r] = l;
+            // ---- O / l -> split planes; this warp takes half of the d_h columns of its rows
             mbar_wait(&o_full[grp], use & 1);
             tc_fence_after();
+            bar_sync_named(1 + grp, 256);
+            l += xo[r];
             const int row = un.rt * kAtcRows + r;
             if (warp_live) {
+                constexpr int CE = DH / 2;                       // columns per warp: 16 or 32
                 const float inv = 1.0f / l;
-#pragma unroll
-                for (int c = 0; c < DH / 32; ++c) {
-                    uint32_t o[32];
-                    tmem_ld32(tb + OCOL + c * 32, o);
-                    tmem_ld_wait();
-                    if (p.nacc == 3) {                               // the three product terms were accumulated separately
-                        uint32_t o1[32], o2[32];
-                        tmem_ld32(tb + OCOL + DH + c * 32, o1);
-                        tmem_ld32(tb + OCOL + 2 * DH + c * 32, o2);
+                uint32_t o[CE];
+                if constexpr (CE == 32) tmem_ld32(tb + OCOL_C + half * CE, o); else tmem_ld16(tb + OCOL_C + half * CE, o);
+                tmem_ld_wait();
+                if (p.nacc == 3) {                               // the three product terms were accumulated separately
+#pragma unroll 1
+                    for (int t = 1; t < 3; ++t) {
+                        uint32_t o1[CE];
+                        if constexpr (CE == 32) tmem_ld32(tb + OCOL_C + t * DH + half * CE, o1); else tmem_ld16(tb + OCOL_C + t * DH + half * CE, o1);
                         tmem_ld_wait();
 #pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            o[j] = __float_as_uint(__uint_as_float(o[j]) + (__uint_as_float(o1[j]) + __uint_as_float(o2[j])));
+                        for (int j = 0; j < CE; ++j) o[j] = __float_as_uint(__uint_as_float(o[j]) + __uint_as_float(o1[j]));
                     }
-                    if (row < S) {
-                        uint32_t oh[16], ol[16];
+                }
+                if (row < S) {
+                    uint32_t oh[CE / 2], ol[CE / 2];
 #pragma unroll
-                        for (int j = 0; j < 16; ++j)
-                            atc_split_pack(__uint_as_float(o[2 * j]) * inv, __uint_as_float(o[2 * j + 1]) * inv, oh[j], ol[j]);
-                        const size_t off = static_cast<size_t>(un.t0 + row) * p.H + un.h * DH + c * 32;
-                        uint4* dh = reinterpret_cast<uint4*>(p.ctx_hi + off);
-                        uint4* dl = reinterpret_cast<uint4*>(p.ctx_lo + off);
+                    for (int j = 0; j < CE / 2; ++j)
+                        atc_split_pack(__uint_as_float(o[2 * j]) * inv, __uint_as_float(o[2 * j + 1]) * inv, oh[j], ol[j]);
+                    const size_t off = static_cast<size_t>(un.t0 + row) * p.H + un.h * DH + half * CE;
+                    uint4* dh = reinterpret_cast<uint4*>(p.ctx_hi + off);
+                    uint4* dl = reinterpret_cast<uint4*>(p.ctx_lo + off);
 #pragma unroll
-                        for (int q4 = 0; q4 < 4; ++q4) {
-                            dh[q4] = make_uint4(oh[4 * q4], oh[4 * q4 + 1], oh[4 * q4 + 2], oh[4 * q4 + 3]);
-                            dl[q4] = make_uint4(ol[4 * q4], ol[4 * q4 + 1], ol[4 * q4 + 2], ol[4 * q4 + 3]);
-                        }
+                    for (int q4 = 0; q4 < CE / 8; ++q4) {
+                        dh[q4] = make_uint4(oh[4 * q4], oh[4 * q4 + 1], oh[4 * q4 + 2], oh[4 * q4 + 3]);
+                        dl[q4] = make_uint4(ol[4 * q4], ol[4 * q4 + 1], ol[4 * q4 + 2], ol[4 * q4 + 3]);
                     }
                 }
             }
+            bar_sync_named(1 + grp, 256);                        // the sums have been read: the exchange slots are free again
         }
     }
 

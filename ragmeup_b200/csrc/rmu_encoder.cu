@@ -467,9 +467,11 @@ struct rmu_encoder {
     SplitOperand X, CTX, X1, FF, QKVP;   // QKVP: q (pre-scaled) | k | v as split planes [T, 3H]
     CUtensorMap att_q_hi{}, att_q_lo{}, att_k_hi{}, att_k_lo{};   // tcgen05 attention: boxes {d_h, 128 rows} / {d_h, 64 rows} of QKVP
     float* PRE = nullptr;                 // fp32 pre-LayerNorm rows (hidden sizes the fused GEMM+LN kernel does not cover)
-    int *d_ids = nullptr, *d_typ = nullptr, *d_cu = nullptr;   // staging for the *_host entry points
+    // staging of the *_host entry points: owned by host_mu alone (NOT part of the activation workspace, which a
+    // concurrent device-pointer caller may free and re-allocate under mu)
+    int *d_ids = nullptr, *d_typ = nullptr, *d_cu = nullptr;
     float* d_out = nullptr;
-    size_t d_out_elems = 0;
+    int stage_tok_cap = 0, stage_seq_cap = 0;
     cudaEvent_t ws_done = nullptr;   // last use of the shared activation workspace (callers on other streams wait on it)
     std::mutex mu;
     std::mutex host_mu;   // the *_host entry points share the staging buffers above: one at a time per handle
@@ -548,11 +550,6 @@ static int ensure_tokens(rmu_encoder* e, int T, int B) {
         if (rc == RMU_OK) rc = make_tmap_2d(&e->att_k_lo, e->QKVP.lo, cap, 3 * H, pitch, DH, 64, 2);
     }
     if (rc == RMU_OK) rc = dev_alloc(e->act_allocs, &e->PRE, static_cast<size_t>(cap) * H);
-    if (rc == RMU_OK) rc = dev_alloc(e->act_allocs, &e->d_ids, static_cast<size_t>(cap));
-    if (rc == RMU_OK) rc = dev_alloc(e->act_allocs, &e->d_typ, static_cast<size_t>(cap));
-    if (rc == RMU_OK) rc = dev_alloc(e->act_allocs, &e->d_cu, static_cast<size_t>(scap));
-    e->d_out_elems = static_cast<size_t>(scap) * std::max(H, e->cfg.num_labels);
-    if (rc == RMU_OK) rc = dev_alloc(e->act_allocs, &e->d_out, e->d_out_elems);
     if (rc != RMU_OK) { free_acts(e); return rc; }
     e->tok_cap = cap;
     e->seq_cap = scap;
@@ -745,6 +742,7 @@ void rmu_encoder_destroy(rmu_encoder* e) {
     if (!e) return;
     cudaDeviceSynchronize();
     free_acts(e);
+    cudaFree(e->d_ids); cudaFree(e->d_typ); cudaFree(e->d_cu); cudaFree(e->d_out);
     for (void* p : e->allocs) cudaFree(p);
     if (e->ws_done) cudaEventDestroy(e->ws_done);
     delete e;
@@ -802,12 +800,21 @@ int rmu_encoder_hidden(rmu_encoder* e, const int32_t* ids, const int32_t* type_i
     return RMU_OK;
 }
 
+// host_mu held: the staging buffers belong to the *_host entry points only
 static int stage_batch(rmu_encoder* e, const int32_t* ids_h, const int32_t* typ_h, const int32_t* cu_h, int B, int T,
                        cudaStream_t st) {
-    {
-        std::lock_guard<std::mutex> g(e->mu);
-        int rc = ensure_tokens(e, T, B);
-        if (rc != RMU_OK) return rc;
+    if (T > e->stage_tok_cap || B + 1 > e->stage_seq_cap) {
+        RMU_CUDA(cudaStreamSynchronize(st));              // earlier *_host calls on this stream are complete (they synchronise)
+        cudaFree(e->d_ids); cudaFree(e->d_typ); cudaFree(e->d_cu); cudaFree(e->d_out);
+        e->d_ids = e->d_typ = e->d_cu = nullptr; e->d_out = nullptr;
+        e->stage_tok_cap = e->stage_seq_cap = 0;
+        const int cap = (std::max(T, 1024) + 127) / 128 * 128, scap = std::max(B + 1, 1024);
+        RMU_CUDA(cudaMalloc(reinterpret_cast<void**>(&e->d_ids), static_cast<size_t>(cap) * sizeof(int)));
+        RMU_CUDA(cudaMalloc(reinterpret_cast<void**>(&e->d_typ), static_cast<size_t>(cap) * sizeof(int)));
+        RMU_CUDA(cudaMalloc(reinterpret_cast<void**>(&e->d_cu), static_cast<size_t>(scap) * sizeof(int)));
+        RMU_CUDA(cudaMalloc(reinterpret_cast<void**>(&e->d_out), static_cast<size_t>(scap) * std::max(e->cfg.hidden, e->cfg.num_labels) * sizeof(float)));
+        e->stage_tok_cap = cap;
+        e->stage_seq_cap = scap;
     }
     RMU_CUDA(cudaMemcpyAsync(e->d_ids, ids_h, static_cast<size_t>(T) * sizeof(int32_t), cudaMemcpyHostToDevice, st));
     if (typ_h) RMU_CUDA(cudaMemcpyAsync(e->d_typ, typ_h, static_cast<size_t>(T) * sizeof(int32_t), cudaMemcpyHostToDevice, st));

@@ -142,3 +142,51 @@ def test_concurrent_callers_share_handles(stack):
     for t in threads:
         t.join()
     assert not errors, errors
+
+
+def test_growth_under_concurrent_search_and_scoring(stack):
+    """Locking holes of round 1 (rmu_index_gather read the corpus pointer without the handle mutex; the *_host encoder
+    entry points staged into buffers another thread's workspace growth could free): one thread keeps ADDING documents
+    (the index reallocates and frees its old corpus) and scoring ever larger batches (the activation workspace is
+    re-allocated) while other threads run MMR searches (search + gather) and score through the host entry points."""
+    import threading
+    from ragmeup_b200.vectorstore import Milvus
+    emb, ce, docs, queries = stack
+    db = Milvus(emb, collection_name="grow")
+    db.add_documents([Document(t, {"source": "s"}) for t in docs[:64]], ids=[f"k{i}" for i in range(64)])
+    probe = docs[3]                                         # an exact copy of a stored text: distance 0, always first
+    pairs = [(queries[0], d) for d in docs[:8]]
+    want_scores = ce.score(pairs)
+    errors, stop = [], threading.Event()
+
+    def writer():
+        try:
+            n = 64
+            for step in range(10):
+                grow = 64 * (step + 1)
+                batch = [Document(docs[(n + j) % len(docs)] + f" #{n + j}", {"source": "s"}) for j in range(grow)]
+                db.add_documents(batch, ids=[f"k{n + j}" for j in range(grow)])
+                n += grow
+                ce.score([(queries[1], d) for d in docs[: 40 * (step + 1)]])      # a larger token batch every time
+        except Exception as e:  # noqa: BLE001
+            errors.append("writer: " + repr(e))
+        finally:
+            stop.set()
+
+    def reader():
+        try:
+            while not stop.is_set():
+                got = db.max_marginal_relevance_search(probe, k=4, fetch_k=12)
+                assert got and got[0].page_content == probe
+                assert np.abs(ce.score(pairs) - want_scores).max() < 1e-6
+        except Exception as e:  # noqa: BLE001
+            errors.append("reader: " + repr(e))
+            stop.set()
+
+    threads = [threading.Thread(target=writer)] + [threading.Thread(target=reader) for _ in range(3)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+    assert len(db) == 64 + sum(64 * (s + 1) for s in range(10))
