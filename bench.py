@@ -103,7 +103,7 @@ class ClockSampler:
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "50",
                                           "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -113,13 +113,23 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
 
+    def wait_rows(self, n: int, timeout: float) -> None:
+        """nvidia-smi takes a good part of a second to print its first row: wait until it is really sampling"""
+        t0 = time.perf_counter()
+        while self.proc is not None and len(self.rows) < n and time.perf_counter() - t0 < timeout:
+            time.sleep(0.01)
+
+    def mark(self) -> None:
+        self.first = len(self.rows)                     # rows from here on belong to the timed region
+
     def stop(self):
+        rows = self.rows[getattr(self, "first", 0):]
         if self.proc is not None:
             self.proc.terminate()
-        sm = [float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
+        sm = [float(r[1]) for r in rows if len(r) >= 8 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
         reasons = set()
-        for r in self.rows:
+        for r in rows:
             if len(r) >= 8:
                 for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
                     if v.lower().startswith("active"):
@@ -296,25 +306,28 @@ def run_gpu(args):
         torch.cuda.synchronize()
 
     # ---------------- timed region: device-resident step
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     for _ in range(args.warmup):
         out_ids, out_scores = step_device()
+    if rank == 0:
+        sampler.wait_rows(1, 3.0)          # nvidia-smi is really sampling before anybody starts the timed region
     barrier()
     launches0 = _lib.launch_count()
     _lib.profile_reset()
     _lib.profile_enable(True)
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
+    # the clock sampler is started during the warm-up (nvidia-smi needs ~1 s before its first row) and only the rows it
+    # prints between here and the end of the timed steps are kept; short steps are repeated (untimed region extended
+    # AFTER ev1) until at least a few samples fell inside GPU work of the same kind
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t_wall0 = time.perf_counter()
+    if rank == 0:
+        sampler.mark()
     ev0.record()
     for _ in range(args.steps):
         out_ids, out_scores = step_device()
     ev1.record()
     barrier()
-    if rank == 0 and time.perf_counter() - t_wall0 < 0.35:
-        time.sleep(0.35 - (time.perf_counter() - t_wall0))      # nvidia-smi needs a few 100 ms periods to report anything
-    clocks = sampler.stop() if rank == 0 else None
     ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -322,6 +335,13 @@ def run_gpu(args):
     _lib.profile_enable(False)
     prof = _lib.profile_read()
     launches = _lib.launch_count() - launches0
+    # short steps: keep the same load running (outside the timed events, the same count on every rank) until the sampler
+    # has seen ~0.3 s of it
+    extra = min(400, max(0, int(np.ceil(300.0 / max(total_ms / args.steps, 1e-3))) - args.steps))
+    for _ in range(extra):
+        step_device()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
 
     # ---------------- e2e through host buffers (every rank runs its part; max over ranks)
     light = os.environ.get("BENCH_LIGHT") == "1"       # launch-list captures under ncu only: no e2e warm-up, no CPU arm

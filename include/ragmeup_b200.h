@@ -79,8 +79,9 @@ const float* rmu_index_data(const rmu_index* idx);
 /* top-k of every query against the whole index.
  *   queries [nq, dim] fp32, out_scores [nq, k] fp32, out_ids [nq, k] int64 = id_offset + row,
  *   missing results (k > size) are id -1 with score -inf (+inf for L2).
- *   stats_h (nullable, host int32[4]): {queries re-run on the exact path, tensor-scan launches,
- *   0, 0}; requesting it makes the call synchronise the stream. */
+ *   stats_h (nullable, host int32[4]): {queries whose certificate failed in the first tensor pass, first-pass
+ *   tensor-scan launches, queries that still needed the exact fp32 CUDA-core scan after the second pass, 0};
+ *   requesting it makes the call synchronise the stream. */
 int rmu_index_search(rmu_index* idx, const float* queries, int nq, int k, int64_t id_offset, int mode,
                      float* out_scores, int64_t* out_ids, int32_t* stats_h, void* stream);
 /* same, HOST buffers in and out (H2D + D2H inside the call, synchronises `stream`) */

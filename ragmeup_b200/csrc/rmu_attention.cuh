@@ -369,3 +369,288 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tq_hi, const __grid_cons
     tc_fence_after();
     if (warp == 1) tmem_dealloc<512>(tmem_base);
 }
+
+// =====================================================================================================================
+// attention_pair_kernel (d_h = 32): the same arithmetic, organised around what measurements of attention_tc_kernel showed
+// to be its limit: the TMA engine delivers about one box ROW (<= 128 B) per 5 cycles per SM, whatever the row length
+// (13.2 B/clk/SM with the 64-byte rows of one d_h = 32 head; 25.6 B/clk/SM in the scan's 128-byte rows), and the kernel
+// spent its 367 us per layer call fetching 19.7 M such rows (K and V twice per sequence, once per query-row tile; 192 rows
+// for 147 keys) while tensor pipe, MUFU and issue slots idled.  Here
+//   * a work item is (sequence, PAIR of adjacent heads): Q, K and V boxes are 128 bytes wide (both heads), SWIZZLE_128B;
+//     the two heads are the two in-flight units (TMEM buffer g = head 2*hp + g); their operands are the same shared-
+//     memory tiles, addressed 64 bytes apart inside the swizzled rows;
+//   * K and V of a work item are loaded once and serve all its query-row tiles; boxes are 32 rows, so 147 keys fetch
+//     160 rows, and a 19-row last tile fetches 32 Q rows;
+// i.e. 480 box rows per (sequence, head) instead of 2048.  Roles: warp 0 TMA, warp 1 S = Q K^T issuer (both heads),
+// warps 2 / 3 the P V issuers of head 0 / 1, then 8 softmax warps per head.
+// =====================================================================================================================
+constexpr int kApThreads = 640;
+constexpr int kApMaxKeys = 160;                // keys (16-aligned) + three O accumulators of 32 columns = 256 TMEM columns
+constexpr int kApRowB = 128;                   // operand row: two heads x 32 halves
+constexpr int kApQSlot = 2 * kAtcRows * kApRowB;   // Q_hi, Q_lo of one query-row tile
+constexpr int kApStateBytes = 512 + 4 * 128 * 4;
+
+struct ApParams {
+    const int* cu;
+    int B, heads, H;
+    int kp;                 // rows per K / V plane of a slot: max_seqlen rounded up to 32 (<= kApMaxKeys)
+    __half* ctx_hi; __half* ctx_lo;
+};
+
+__global__ void __launch_bounds__(kApThreads, 1)
+attention_pair_kernel(const __grid_constant__ CUtensorMap t_hi, const __grid_constant__ CUtensorMap t_lo, const ApParams p) {
+    constexpr int DH = 32;
+    constexpr uint32_t LAYOUT = 2u;                        // SWIZZLE_128B
+    constexpr uint32_t SBO = 8 * kApRowB;
+    constexpr int OCOL = kAtcBufCols - 3 * DH;             // 160
+    constexpr uint32_t IDESC_O = umma_idesc(0 /*f16*/, kAtcRows, DH) | (1u << 16);   // B = V, MN-major
+
+    extern __shared__ __align__(1024) uint8_t ap_smem_raw[];     // two K / V slots + two Q slots use all 227 KB at 160 keys:
+    uint8_t* smem = ap_smem_raw;                                  // no room for an alignment pad, the declaration must deliver it
+    if ((smem_u32(ap_smem_raw) & 1023u) != 0u) __trap();
+    const int kvplane = p.kp * kApRowB;                    // one of K_hi, K_lo, V_hi, V_lo
+    const int kvslot = 4 * kvplane;
+    uint8_t* kvring = smem;                                // 2 slots
+    uint8_t* qring = smem + 2 * kvslot;                    // 2 slots
+    uint8_t* state = qring + 2 * kApQSlot;
+    uint64_t* kv_full = reinterpret_cast<uint64_t*>(state);
+    uint64_t* kv_empty = kv_full + 2;
+    uint64_t* q_full = kv_empty + 2;
+    uint64_t* q_empty = q_full + 2;
+    uint64_t* s_full = q_empty + 2;                        // [2] S of head g is complete
+    uint64_t* p_full = s_full + 2;                         // [2][8] chunk c of P of head g is written
+    uint64_t* o_full = p_full + 2 * kAtcMaxChunks;         // [2]
+    uint64_t* s_free = o_full + 2;                         // [2] the P V MMAs that read buffer g have completed
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_free + 2);
+    float* xch = reinterpret_cast<float*>(state + 512);    // [2 heads][2 halves][128 rows]
+
+    const int warp = threadIdx.x >> 5;
+    const unsigned lane = lane_id();
+    const int hpairs = p.heads >> 1;
+    const int nwork = p.B * hpairs;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 2); mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1);
+            mbar_init(&s_full[i], 1); mbar_init(&o_full[i], 1); mbar_init(&s_free[i], 1);
+            for (int c = 0; c < kAtcMaxChunks; ++c) mbar_init(&p_full[i * kAtcMaxChunks + c], 1);
+        }
+        fence_mbar_init();
+        prefetch_tmap(&t_hi); prefetch_tmap(&t_lo);
+    }
+    if (warp == 1) tmem_alloc<512>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // =========================== TMA producer ===========================
+        if (lane == 0) {
+            int kvi = 0, qi = 0;
+            for (int w = blockIdx.x; w < nwork; w += gridDim.x) {
+                const int b = w / hpairs, hp = w % hpairs;
+                const int t0 = __ldg(p.cu + b), S = __ldg(p.cu + b + 1) - t0;
+                const int col = hp * 64;
+                const int kvs = kvi & 1;
+                mbar_wait(&kv_empty[kvs], ((kvi >> 1) & 1) ^ 1);
+                const int nkb = (S + 31) >> 5;
+                uint8_t* kb0 = kvring + kvs * kvslot;
+                mbar_arrive_expect_tx(&kv_full[kvs], static_cast<uint32_t>(4 * nkb * 32 * kApRowB));
+                for (int kb = 0; kb < nkb; ++kb) {
+                    uint8_t* d = kb0 + kb * 32 * kApRowB;
+                    tma_load_2d(d, &t_hi, p.H + col, t0 + kb * 32, &kv_full[kvs], kEvictNormal);
+                    tma_load_2d(d + kvplane, &t_lo, p.H + col, t0 + kb * 32, &kv_full[kvs], kEvictNormal);
+                    tma_load_2d(d + 2 * kvplane, &t_hi, 2 * p.H + col, t0 + kb * 32, &kv_full[kvs], kEvictNormal);
+                    tma_load_2d(d + 3 * kvplane, &t_lo, 2 * p.H + col, t0 + kb * 32, &kv_full[kvs], kEvictNormal);
+                }
+                for (int r0 = 0; r0 < S; r0 += kAtcRows, ++qi) {
+                    const int qs = qi & 1;
+                    mbar_wait(&q_empty[qs], ((qi >> 1) & 1) ^ 1);
+                    const int nqb = (min(kAtcRows, S - r0) + 31) >> 5;
+                    uint8_t* q0 = qring + qs * kApQSlot;
+                    mbar_arrive_expect_tx(&q_full[qs], static_cast<uint32_t>(2 * nqb * 32 * kApRowB));
+                    for (int qb = 0; qb < nqb; ++qb) {
+                        tma_load_2d(q0 + qb * 32 * kApRowB, &t_hi, col, t0 + r0 + qb * 32, &q_full[qs], kEvictNormal);
+                        tma_load_2d(q0 + kAtcRows * kApRowB + qb * 32 * kApRowB, &t_lo, col, t0 + r0 + qb * 32, &q_full[qs], kEvictNormal);
+                    }
+                }
+                ++kvi;
+            }
+        }
+    } else if (warp == 1) {
+        // =========================== S = Q K^T issuer, both heads ===========================
+        if (lane == 0) {
+            int kvi = 0, qi = 0;
+            uint32_t cnt = 0;                                    // tiles issued so far (the same for both heads)
+            for (int w = blockIdx.x; w < nwork; w += gridDim.x) {
+                const int b = w / hpairs;
+                const int S = __ldg(p.cu + b + 1) - __ldg(p.cu + b);
+                const int kvs = kvi & 1;
+                mbar_wait(&kv_full[kvs], (kvi >> 1) & 1);
+                const uint32_t kh = smem_u32(kvring + kvs * kvslot), kl = kh + kvplane;
+                const uint32_t idesc_s = umma_idesc(0 /*f16*/, kAtcRows, ((S + 15) >> 4) << 4);
+                for (int r0 = 0; r0 < S; r0 += kAtcRows, ++qi, ++cnt) {
+                    const int qs = qi & 1;
+                    mbar_wait(&q_full[qs], (qi >> 1) & 1);
+                    const uint32_t qh = smem_u32(qring + qs * kApQSlot), ql = qh + kAtcRows * kApRowB;
+#pragma unroll
+                    for (int g = 0; g < 2; ++g) {
+                        mbar_wait(&s_free[g], (cnt & 1) ^ 1);    // P V of this head's previous tile no longer reads the buffer
+                        tc_fence_after();
+                        const uint32_t d_addr = tmem_base + g * kAtcBufCols;
+#pragma unroll
+                        for (int term = 0; term < 3; ++term) {
+                            const uint32_t a = (term == 1 ? ql : qh) + g * 64, bb = (term == 2 ? kl : kh) + g * 64;
+#pragma unroll
+                            for (int k = 0; k < 2; ++k)
+                                mma_f16_ss(d_addr, atc_desc(a + k * 32, SBO, LAYOUT), atc_desc(bb + k * 32, SBO, LAYOUT), idesc_s,
+                                           (term | k) != 0 ? 1u : 0u);
+                        }
+                        tc_commit(&s_full[g]);
+                    }
+                    tc_commit(&q_empty[qs]);                     // the Q tile has been read by both heads' MMAs
+                }
+                ++kvi;
+            }
+        }
+    } else if (warp < 4) {
+        // =========================== O = P V issuer of head g ===========================
+        if (lane == 0) {
+            const int g = warp - 2;
+            int kvi = 0;
+            uint32_t ppar = 0u;                                  // bit c = parity the next wait on p_full[g][c] uses
+            for (int w = blockIdx.x; w < nwork; w += gridDim.x) {
+                const int b = w / hpairs;
+                const int S = __ldg(p.cu + b + 1) - __ldg(p.cu + b);
+                const int kvs = kvi & 1;
+                const uint32_t vh = smem_u32(kvring + kvs * kvslot + 2 * kvplane) + g * 64, vl = vh + kvplane;
+                const uint32_t pbase = tmem_base + g * kAtcBufCols;
+                const uint32_t d0 = pbase + OCOL, d1 = d0 + DH, d2 = d0 + 2 * DH;
+                const int nk16 = (S + 15) >> 4, nchunk = (S + 31) >> 5;
+                for (int r0 = 0; r0 < S; r0 += kAtcRows) {
+                    for (int c = 0; c < nchunk; ++c) {
+                        mbar_wait(&p_full[g * kAtcMaxChunks + c], (ppar >> c) & 1u);
+                        ppar ^= 1u << c;
+                        tc_fence_after();
+                        for (int j16 = 2 * c; j16 < min(2 * c + 2, nk16); ++j16) {
+                            const uint32_t a_hi = pbase + 32 * c + 8 * (j16 & 1), a_lo = a_hi + 16;
+                            const uint64_t bh = atc_desc(vh + j16 * 16 * kApRowB, SBO, LAYOUT), bl = atc_desc(vl + j16 * 16 * kApRowB, SBO, LAYOUT);
+                            const uint32_t acc = j16 != 0 ? 1u : 0u;
+                            mma_f16_ts(d0, a_hi, bh, IDESC_O, acc);
+                            mma_f16_ts(d1, a_lo, bh, IDESC_O, acc);
+                            mma_f16_ts(d2, a_hi, bl, IDESC_O, acc);
+                        }
+                    }
+                    tc_commit(&o_full[g]);
+                    tc_commit(&s_free[g]);
+                    if (r0 + kAtcRows >= S) tc_commit(&kv_empty[kvs]);   // last tile of the work item: K / V slot free (both heads commit)
+                }
+                ++kvi;
+            }
+        }
+    } else {
+        // =========================== softmax + output of head g: thread = query row, two warps per row ===========================
+        const int g = (warp - 4) >> 3;
+        const int half = ((warp - 4) >> 2) & 1;                  // which chunks (c & 1) and which half of O's columns
+        const int quad = warp & 3;
+        const int r = quad * 32 + static_cast<int>(lane);
+        const int htid = ((warp - 4) & 3) * 32 + static_cast<int>(lane);
+        float* xm = xch + (g * 2 + half) * kAtcRows;
+        const float* xo = xch + (g * 2 + (half ^ 1)) * kAtcRows;
+        const uint32_t tb = tmem_addr(tmem_base, quad * 32, g * kAtcBufCols);
+        uint32_t cnt = 0;
+        for (int w = blockIdx.x; w < nwork; w += gridDim.x) {
+            const int b = w / hpairs, hp = w % hpairs;
+            const int t0 = __ldg(p.cu + b), S = __ldg(p.cu + b + 1) - t0;
+            const int nchunk = (S + 31) >> 5;
+            for (int r0 = 0; r0 < S; r0 += kAtcRows, ++cnt) {
+                const bool warp_live = r0 + quad * 32 < S;
+                mbar_wait(&s_full[g], cnt & 1);
+                tc_fence_after();
+                float m = -INFINITY;
+                if (warp_live) {
+                    for (int c = half; c < nchunk; c += 2) {
+                        uint32_t sv[32];
+                        tmem_ld32(tb + c * 32, sv);
+                        tmem_ld_wait();
+                        if (c * 32 + 32 <= S) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) m = fmaxf(m, __uint_as_float(sv[j]));
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) m = fmaxf(m, c * 32 + j < S ? __uint_as_float(sv[j]) : -INFINITY);
+                        }
+                    }
+                }
+                xm[r] = m;
+                bar_sync_named(1 + g, 256);
+                m = fmaxf(m, xo[r]);
+                bar_sync_named(1 + g, 256);
+                float l = 0.f;
+                for (int c = half; c < nchunk; c += 2) {
+                    if (warp_live) {
+                        uint32_t sv[32];
+                        tmem_ld32(tb + c * 32, sv);
+                        tmem_ld_wait();
+                        uint32_t ph[16], pl[16];
+                        const bool tail = c * 32 + 32 > S;
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            float a = atc_exp2(__uint_as_float(sv[2 * j]) - m), bq = atc_exp2(__uint_as_float(sv[2 * j + 1]) - m);
+                            if (tail) {
+                                if (c * 32 + 2 * j >= S) a = 0.f;
+                                if (c * 32 + 2 * j + 1 >= S) bq = 0.f;
+                            }
+                            l += a + bq;
+                            atc_split_pack(a, bq, ph[j], pl[j]);
+                        }
+                        tmem_st16(tb + c * 32, ph);
+                        tmem_st16(tb + c * 32 + 16, pl);
+                        tmem_st_wait();
+                    }
+                    tc_fence_before();
+                    bar_sync_named(3 + g * 2 + half, 128);
+                    if (htid == 0) mbar_arrive(&p_full[g * kAtcMaxChunks + c]);
+                }
+                xm[r] = l;
+                mbar_wait(&o_full[g], cnt & 1);
+                tc_fence_after();
+                bar_sync_named(1 + g, 256);
+                l += xo[r];
+                const int row = r0 + r;
+                if (warp_live) {
+                    const float inv = 1.0f / l;
+                    uint32_t o[16];
+                    tmem_ld16(tb + OCOL + half * 16, o);
+                    tmem_ld_wait();
+#pragma unroll 1
+                    for (int t = 1; t < 3; ++t) {
+                        uint32_t o1[16];
+                        tmem_ld16(tb + OCOL + t * DH + half * 16, o1);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) o[j] = __float_as_uint(__uint_as_float(o[j]) + __uint_as_float(o1[j]));
+                    }
+                    if (row < S) {
+                        uint32_t oh[8], ol[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            atc_split_pack(__uint_as_float(o[2 * j]) * inv, __uint_as_float(o[2 * j + 1]) * inv, oh[j], ol[j]);
+                        const size_t off = static_cast<size_t>(t0 + row) * p.H + (2 * hp + g) * DH + half * 16;
+                        uint4* dh = reinterpret_cast<uint4*>(p.ctx_hi + off);
+                        uint4* dl = reinterpret_cast<uint4*>(p.ctx_lo + off);
+                        dh[0] = make_uint4(oh[0], oh[1], oh[2], oh[3]); dh[1] = make_uint4(oh[4], oh[5], oh[6], oh[7]);
+                        dl[0] = make_uint4(ol[0], ol[1], ol[2], ol[3]); dl[1] = make_uint4(ol[4], ol[5], ol[6], ol[7]);
+                    }
+                }
+                bar_sync_named(1 + g, 256);
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (warp == 1) tmem_dealloc<512>(tmem_base);
+}

@@ -466,6 +466,7 @@ struct rmu_encoder {
     std::vector<void*> act_allocs;
     SplitOperand X, CTX, X1, FF, QKVP;   // QKVP: q (pre-scaled) | k | v as split planes [T, 3H]
     CUtensorMap att_q_hi{}, att_q_lo{}, att_k_hi{}, att_k_lo{};   // tcgen05 attention: boxes {d_h, 128 rows} / {d_h, 64 rows} of QKVP
+    CUtensorMap att_p_hi{}, att_p_lo{};                           // head-pair attention (d_h = 32): boxes {64 halves, 32 rows}
     float* PRE = nullptr;                 // fp32 pre-LayerNorm rows (hidden sizes the fused GEMM+LN kernel does not cover)
     // staging of the *_host entry points: owned by host_mu alone (NOT part of the activation workspace, which a
     // concurrent device-pointer caller may free and re-allocate under mu)
@@ -548,6 +549,8 @@ static int ensure_tokens(rmu_encoder* e, int T, int B) {
         if (rc == RMU_OK) rc = make_tmap_2d(&e->att_q_lo, e->QKVP.lo, cap, 3 * H, pitch, DH, kAtcRows, 2);
         if (rc == RMU_OK) rc = make_tmap_2d(&e->att_k_hi, e->QKVP.hi, cap, 3 * H, pitch, DH, 64, 2);
         if (rc == RMU_OK) rc = make_tmap_2d(&e->att_k_lo, e->QKVP.lo, cap, 3 * H, pitch, DH, 64, 2);
+        if (rc == RMU_OK && DH == 32) rc = make_tmap_2d(&e->att_p_hi, e->QKVP.hi, cap, 3 * H, pitch, 64, 32, 2);
+        if (rc == RMU_OK && DH == 32) rc = make_tmap_2d(&e->att_p_lo, e->QKVP.lo, cap, 3 * H, pitch, 64, 32, 2);
     }
     if (rc == RMU_OK) rc = dev_alloc(e->act_allocs, &e->PRE, static_cast<size_t>(cap) * H);
     if (rc != RMU_OK) { free_acts(e); return rc; }
@@ -575,7 +578,8 @@ static int run_encoder(rmu_encoder* e, const int32_t* ids, const int32_t* type_i
     const float scale = 1.0f / sqrtf(static_cast<float>(DH));
     for (int l = 0; l < c.layers; ++l) {
         EncLayer& L = e->layers[l];
-        // RMU_ATTN_MODE: 0 = tcgen05 attention where the shape allows it (else the mma.sync kernel), 3 = always mma.sync
+        // RMU_ATTN_MODE: 0 = tcgen05 attention where the shape allows it (head-pair kernel, else per-head kernel, else mma.sync),
+        // 1 = never the head-pair kernel, 3 = always mma.sync
         static const int attn_mode = [] { const char* e = getenv("RMU_ATTN_MODE"); return e ? atoi(e) : 0; }();
         GemmParams g{};
         g.M = T; g.N = 3 * H; g.K = H; g.bias = L.bqkv;
@@ -591,7 +595,18 @@ static int run_encoder(rmu_encoder* e, const int32_t* ids, const int32_t* type_i
             const int kp = (max_seqlen + 63) / 64 * 64;
             const int slot_bytes = 2 * kAtcRows * DH * 2 + 4 * kp * DH * 2;
             const int nslots = std::min(kAtcMaxSlots, (227 * 1024 - 1024 - kAtcStateBytes) / slot_bytes);
-            if (attn_mode == 0 && max_seqlen <= kAtcBufCols - DH && nslots >= 2) {
+            if (attn_mode == 0 && DH == 32 && c.heads % 2 == 0 && max_seqlen <= kApMaxKeys) {
+                // head-pair kernel: 128-byte operand rows, K / V shared by the query-row tiles of a sequence
+                ApParams ap{};
+                ap.cu = cu; ap.B = B; ap.heads = c.heads; ap.H = H; ap.kp = (max_seqlen + 31) / 32 * 32;
+                ap.ctx_hi = e->CTX.hi; ap.ctx_lo = e->CTX.lo;
+                // no alignment pad: the dynamic shared array is declared __align__(1024) and the kernel traps if the base is not
+                const size_t smem = 2 * static_cast<size_t>(4 * ap.kp * kApRowB) + 2 * kApQSlot + kApStateBytes;
+                const long long nwork = static_cast<long long>(B) * (c.heads / 2);
+                const unsigned grid = static_cast<unsigned>(std::min<long long>(e->sms, nwork));
+                RMU_CUDA(cudaFuncSetAttribute(attention_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+                attention_pair_kernel<<<grid, kApThreads, smem, st>>>(e->att_p_hi, e->att_p_lo, ap);
+            } else if ((attn_mode == 0 || attn_mode == 1) && max_seqlen <= kAtcBufCols - DH && nslots >= 2) {
                 AtcParams ap{};
                 ap.cu = cu; ap.B = B; ap.heads = c.heads; ap.H = H; ap.row_tiles = (max_seqlen + kAtcRows - 1) / kAtcRows;
                 ap.kp = kp; ap.nslots = nslots; ap.ctx_hi = e->CTX.hi; ap.ctx_lo = e->CTX.lo;

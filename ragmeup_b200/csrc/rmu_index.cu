@@ -647,6 +647,8 @@ static int keep_for_k(int k) {
 
 // one scan launch: NQ queries (MMA N); CTA pairs keep NQ/2 query rows resident per CTA, single CTAs all NQ
 struct ScanGeom { int nq, nstages, pair; size_t smem; };
+constexpr int kPass2MaxQ = 256;         // flagged queries the second pass takes per search (more stay flagged)
+constexpr int kPass2PoolCap = 16384;    // rows a flagged query may collect; more -> the exact scan answers
 
 static int env_int(const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; }
 static int scan_kd() { static const int v = env_int("RMU_SCAN_KD", 2) == 1 ? 1 : 2; return v; }          // boxes per stage
@@ -883,6 +885,14 @@ int rmu_index_search(rmu_index* idx, const float* queries, int nq, int k, int64_
     const size_t o_scan = tensor_ok ? carve(sizeof(unsigned long long) * max_lists * kListCap) : 0;
     const size_t o_cnt = tensor_ok ? carve(sizeof(int) * max_lists) : 0;
     const size_t o_floor = tensor_ok ? carve(sizeof(float) * max_lists) : 0;
+    // second pass (flagged queries, AUTO mode): compacted queries + thresholds + per-query pools
+    const int p2max = (tensor_ok && mode == RMU_SEARCH_AUTO) ? std::min(nq, kPass2MaxQ) : 0;
+    const size_t o_tau2 = carve(sizeof(float) * nq);
+    const size_t o_qbuf = carve(sizeof(float) * static_cast<size_t>(p2max) * D);
+    const size_t o_taub = carve(sizeof(float) * std::max(p2max, 1));
+    const size_t o_pcnt = carve(sizeof(int) * std::max(p2max, 1));
+    const size_t o_pool = carve(sizeof(unsigned long long) * static_cast<size_t>(p2max) * kPass2PoolCap);
+    const size_t o_qmap2 = carve(sizeof(int) * nq);
     const size_t o_exact = carve(sizeof(unsigned long long) * std::max(nchunks, 1) * static_cast<size_t>(nq) * keepx);
     int rc = ensure_ws(idx, off);
     if (rc != RMU_OK) return rc;
@@ -894,6 +904,13 @@ int rmu_index_search(rmu_index* idx, const float* queries, int nq, int k, int64_
     unsigned long long* d_exact = reinterpret_cast<unsigned long long*>(ws + o_exact);
     int* d_cnt = reinterpret_cast<int*>(ws + o_cnt);
     float* d_floor = reinterpret_cast<float*>(ws + o_floor);
+    float* d_tau2 = reinterpret_cast<float*>(ws + o_tau2);
+    float* d_qbuf = reinterpret_cast<float*>(ws + o_qbuf);
+    float* d_taub = reinterpret_cast<float*>(ws + o_taub);
+    int* d_pcnt = reinterpret_cast<int*>(ws + o_pcnt);
+    unsigned long long* d_pool = reinterpret_cast<unsigned long long*>(ws + o_pool);
+    int* d_qmap2 = reinterpret_cast<int*>(ws + o_qmap2);
+    int* d_nsel2 = d_nsel + 1;                               // queries still flagged after the second pass
 
     int scan_launches = 0;
 
@@ -932,7 +949,7 @@ int rmu_index_search(rmu_index* idx, const float* queries, int nq, int k, int64_
             fp.x = idx->x; fp.n = N; fp.dim = D; fp.metric = idx->metric; fp.q = qbase; fp.q0 = q0;
             fp.k = k; fp.id_offset = id_offset; fp.stats_bits = idx->max_norm_bits;
             fp.eps_rel = 2.2e-3f;   // > 2^-9: both TF32 operands truncated to 10 mantissa bits
-            fp.out_scores = out_scores; fp.out_ids = reinterpret_cast<long long*>(out_ids); fp.flags = d_flags;
+            fp.out_scores = out_scores; fp.out_ids = reinterpret_cast<long long*>(out_ids); fp.flags = d_flags; fp.tau2 = d_tau2;
             const size_t sel_smem = sizeof(unsigned long long) * kSel2Cap + static_cast<size_t>(D) * sizeof(float);
             RMU_CUDA(cudaFuncSetAttribute(select_rescore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
             { ProfScope _ps(PROF_FINALIZE, st);
@@ -944,6 +961,44 @@ int rmu_index_search(rmu_index* idx, const float* queries, int nq, int k, int64_
         compact_flags_kernel<<<1, 32, 0, st>>>(d_flags, nq, d_qmap, d_nsel);
         count_launch();
         RMU_CHECK_LAUNCH();
+        if (p2max > 0) {
+            // ---- second pass for the queries whose certificate failed (near-duplicate heavy neighbourhoods): one more
+            // tensor scan that collects EVERY row whose coarse key can still reach the k-th exact score of the first pass
+            // (threshold = that score - eps), exact re-score of those pools -> exact top-k.  Worst case = 2 scans instead of
+            // the 8+ CUDA-core passes of the exact scan; when nothing is flagged the launches below exit at once.
+            pool_prepare_kernel<<<p2max, 128, 0, st>>>(queries, d_qmap, d_nsel, D, d_tau2, d_qbuf, d_taub, d_pcnt);
+            count_launch();
+            RMU_CHECK_LAUNCH();
+            for (int j0 = 0; j0 < p2max;) {
+                const ScanGeom geo = scan_geometry(D, p2max - j0);
+                const int nql = std::min(p2max - j0, geo.nq);
+                const int grid = geo.pair ? 2 * std::min(idx->sms / 2, (ntiles + 1) / 2) : std::min(idx->sms, ntiles);
+                CUtensorMap tq;
+                rc = make_tmap_2d(&tq, d_qbuf + static_cast<size_t>(j0) * D, static_cast<uint64_t>(nql), static_cast<uint64_t>(D),
+                                  static_cast<uint64_t>(D) * sizeof(float), 32, static_cast<uint32_t>(geo.nq / (geo.pair ? 2 : 1)), 4);
+                if (rc != RMU_OK) return rc;
+                ScanParams sp{};
+                sp.nq = nql; sp.dim = D; sp.n = N; sp.ntiles = ntiles; sp.nstages = geo.nstages; sp.metric = idx->metric;
+                sp.rscale = idx->rscale; sp.rbias = idx->rbias; sp.stats_bits = idx->max_norm_bits;
+                sp.lists = d_scan; sp.counts = d_cnt; sp.floors = d_floor; sp.gmax = idx->gmax; sp.epoch = idx->epoch; sp.groups = 0;
+                sp.fixed_tau = d_taub + j0; sp.pool = d_pool + static_cast<size_t>(j0) * kPass2PoolCap; sp.pool_cnt = d_pcnt + j0;
+                sp.pool_cap = kPass2PoolCap; sp.nq_dev = d_nsel; sp.q_off = j0;
+                rc = scan_dispatch(geo, idx->tmap, tq, sp, grid, st);
+                if (rc != RMU_OK) return rc;
+                j0 += nql;
+            }
+            PoolParams pp{};
+            pp.pool = d_pool; pp.pool_cnt = d_pcnt; pp.pool_cap = kPass2PoolCap; pp.qmap = d_qmap; pp.nsel = d_nsel; pp.max_slots = p2max;
+            pp.x = idx->x; pp.dim = D; pp.metric = idx->metric; pp.q = queries; pp.k = k; pp.id_offset = id_offset;
+            pp.out_scores = out_scores; pp.out_ids = reinterpret_cast<long long*>(out_ids); pp.flags = d_flags;
+            { ProfScope _ps(PROF_FINALIZE, st);
+            pool_rescore_kernel<<<p2max, kSel2Threads, static_cast<size_t>(D) * sizeof(float), st>>>(pp); }
+            count_launch();
+            RMU_CHECK_LAUNCH();
+            compact_flags_kernel<<<1, 32, 0, st>>>(d_flags, nq, d_qmap2, d_nsel2);
+            count_launch();
+            RMU_CHECK_LAUNCH();
+        }
     }
 
     if (!tensor_ok || mode == RMU_SEARCH_AUTO) {
@@ -954,7 +1009,8 @@ int rmu_index_search(rmu_index* idx, const float* queries, int nq, int k, int64_
         if (N > 0) {
             ExactParams ep{};
             ep.x = idx->x; ep.n = N; ep.dim = D; ep.metric = idx->metric; ep.q = queries;
-            ep.qmap = tensor_ok ? d_qmap : nullptr; ep.nsel = tensor_ok ? d_nsel : nullptr; ep.nq_total = nq;
+            ep.qmap = tensor_ok ? (p2max > 0 ? d_qmap2 : d_qmap) : nullptr;
+            ep.nsel = tensor_ok ? (p2max > 0 ? d_nsel2 : d_nsel) : nullptr; ep.nq_total = nq;
             ep.lists = d_exact; ep.keep = keepx; ep.nchunks = nchunks;
             const int ngroups = (nq + kExactQT - 1) / kExactQT;
             int gy = tensor_ok ? 1 : std::min(ngroups, std::max(1, (2 * idx->sms + nchunks - 1) / nchunks));
@@ -979,13 +1035,15 @@ int rmu_index_search(rmu_index* idx, const float* queries, int nq, int k, int64_
     }
 
     if (stats_h) {
-        int nsel = tensor_ok ? 0 : nq;
+        int nsel[2] = {tensor_ok ? 0 : nq, tensor_ok ? 0 : nq};
         if (tensor_ok) {
-            RMU_CUDA(cudaMemcpyAsync(&nsel, d_nsel, sizeof(int), cudaMemcpyDeviceToHost, st));
+            RMU_CUDA(cudaMemcpyAsync(nsel, d_nsel, (p2max > 0 ? 2 : 1) * sizeof(int), cudaMemcpyDeviceToHost, st));
             RMU_CUDA(cudaStreamSynchronize(st));
+            if (p2max == 0) nsel[1] = nsel[0];
         }
-        stats_h[0] = nsel;
+        stats_h[0] = nsel[0];          // certificate failed in the first pass
         stats_h[1] = scan_launches;
+        stats_h[2] = nsel[1];          // still unanswered after the second pass: went to the exact CUDA-core scan
     }
     RMU_CUDA(cudaEventRecord(idx->ws_done, st));
     return RMU_OK;

@@ -63,6 +63,14 @@ struct ScanParams {
     unsigned epoch;
     int groups;                // 0: no exchange (grids smaller than the group count)
     float* dbg;                // diagnostics: raw accumulators of the first 256 rows, [NQ][256]
+    // second pass for queries whose certificate failed ("pool mode", fixed_tau != nullptr): every row whose coarse key
+    // beats the query's FIXED threshold is appended to a per-query pool; no lists, no exchange
+    const float* fixed_tau;    // [NQ] thresholds of the launch's query slots
+    unsigned long long* pool;  // [NQ][pool_cap]
+    int* pool_cnt;             // [NQ] entries appended (may exceed pool_cap: overflow, the query stays flagged)
+    int pool_cap;
+    const int* nq_dev;         // nullable: live queries of the pass (device count of flagged queries)
+    int q_off;                 // this launch serves slots q_off .. q_off + nq - 1 of them
     int ablate;                // profiling only: bit0 skip the MMAs, bit1 skip the epilogue work
 };
 
@@ -141,6 +149,12 @@ scan_rows_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     int* cnt_s = reinterpret_cast<int*>(state + 1024);          // [NQ] entries in each list of this CTA
     float* floor_s = reinterpret_cast<float*>(state + 1536);    // [NQ] largest score each list ever cut away
 
+    int nq_live = p.nq;
+    if (p.nq_dev != nullptr) {                           // second pass: nothing flagged in this launch's range -> nothing to do
+        nq_live = min(p.nq, __ldg(p.nq_dev) - p.q_off);
+        if (nq_live <= 0) return;                        // uniform over the grid: no barrier, no TMEM allocation yet
+    }
+    const bool pool_mode = p.fixed_tau != nullptr;
     const int warp = threadIdx.x >> 5;
     const unsigned lane = lane_id();
     const int rank = PAIR ? static_cast<int>(cluster_ctarank()) : 0;   // 0 = leader (issues the MMAs)
@@ -245,9 +259,9 @@ scan_rows_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         const bool unit_rows = __uint_as_float(__ldg(p.stats_bits + 1)) < 1e-6f;
         const bool has_sc = p.metric == RMU_METRIC_COSINE && !unit_rows;
         const bool has_bi = p.metric == RMU_METRIC_L2 && !unit_rows;
-        const bool qlive = et < NQ && et < p.nq;
+        const bool qlive = et < NQ && et < nq_live;
         if (et < NQ) {
-            tau_s[et] = qlive ? -INFINITY : INFINITY;
+            tau_s[et] = qlive ? (pool_mode ? __ldg(p.fixed_tau + et) : -INFINITY) : INFINITY;
             cnt_s[et] = 0;
             floor_s[et] = -INFINITY;
         }
@@ -304,14 +318,19 @@ scan_rows_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                     for (int j = 0; j < CW; ++j) {
                         if (m & (1u << j)) {
                             const int ql = c * CW + j;
-                            const int pos = atomicAdd(&cnt_s[ql], 1);
-                            mylists[ql * kListCap + pos] = make_key(v[j], static_cast<uint32_t>(row));
-                            mine |= pos >= kListTrig;
+                            if (pool_mode) {
+                                const int pos = atomicAdd(p.pool_cnt + ql, 1);
+                                if (pos < p.pool_cap) p.pool[static_cast<size_t>(ql) * p.pool_cap + pos] = make_key(v[j], static_cast<uint32_t>(row));
+                            } else {
+                                const int pos = atomicAdd(&cnt_s[ql], 1);
+                                mylists[ql * kListCap + pos] = make_key(v[j], static_cast<uint32_t>(row));
+                                mine |= pos >= kListTrig;
+                            }
                         }
                     }
                 }
             }
-            if (p.ablate & 2) continue;
+            if ((p.ablate & 2) || pool_mode) continue;
             // ---- tile boundary: sort + cut the lists that grew past kListTrig (every sort publishes the list's 16th key, so
             // the thresholds of all CTAs rise together: ~5 sorts per list over a 10M-row scan, most of them in the first tiles)
             const bool any = bar_red_or_named(1, ETH, mine);
@@ -343,7 +362,7 @@ scan_rows_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                 tau_s[et] = fmaxf(tg, floor_s[et]);
             }
         }
-        if (et < NQ) {
+        if (et < NQ && !pool_mode) {
             p.counts[cta * NQ + et] = cnt_s[et];
             p.floors[cta * NQ + et] = floor_s[et];
         }
@@ -379,6 +398,7 @@ struct SelectParams {
     const unsigned* stats_bits;   // [0] max ||x|| , [1] max | ||x||^2 - 1 |
     float eps_rel;
     float* out_scores; long long* out_ids; int* flags;
+    float* tau2;               // [nq] per query: the coarse-key threshold a second pass must use when the query is flagged
 };
 
 // exact_metric with the four fmaf chains of one (query, row) pair spread over the four lanes of a quad (lane & 3 = chain):
@@ -567,8 +587,100 @@ __global__ void __launch_bounds__(kSel2Threads) select_rescore_kernel(const Sele
                 // unit rows: cosine / L2 keys were scanned as inner products, exact to 1e-6 (||x||^2 = 1 +- 1e-6)
                 const float eps = p.eps_rel * scale + 1e-6f * (1.f + fabsf(kth_key)) + (unit ? 4e-6f * (1.f + qnorm) : 0.f);
                 if (!(bound + eps < kth_key)) flag = 1;
+                // every row whose exact score reaches the k-th candidate's has a coarse key above this:
+                if (p.tau2 != nullptr) p.tau2[qg] = kth_key - eps - 1e-6f * (1.f + fabsf(kth_key));
             }
+            if (flag && ncand < p.k && p.tau2 != nullptr) p.tau2[qg] = -INFINITY;   // not even k candidates: everything qualifies
         }
         p.flags[qg] = flag;
     }
+}
+
+
+// =====================================================================================================
+// second pass for flagged queries: gather them, then (after the pool-mode scan) re-score their pools exactly
+// =====================================================================================================
+// block j < *nsel: copy flagged query qmap[j] into slot j of qbuf, its threshold into taubuf[j], clear its pool counter
+__global__ void pool_prepare_kernel(const float* __restrict__ q, const int* __restrict__ qmap, const int* __restrict__ nsel, int dim,
+                                    const float* __restrict__ tau2, float* __restrict__ qbuf, float* __restrict__ taubuf,
+                                    int* __restrict__ pool_cnt) {
+    const int j = blockIdx.x;
+    if (j >= *nsel) return;
+    const int qg = qmap[j];
+    for (int d = threadIdx.x; d < dim; d += blockDim.x) qbuf[static_cast<size_t>(j) * dim + d] = q[static_cast<size_t>(qg) * dim + d];
+    if (threadIdx.x == 0) { taubuf[j] = tau2[qg]; pool_cnt[j] = 0; }
+}
+
+struct PoolParams {
+    unsigned long long* pool; const int* pool_cnt; int pool_cap;
+    const int* qmap; const int* nsel; int max_slots;   // flagged queries beyond max_slots stay flagged
+    const float* x; int dim; int metric;
+    const float* q;            // all queries [nq, dim]
+    int k; long long id_offset;
+    float* out_scores; long long* out_ids; int* flags;
+};
+
+// block j: every row of the pool (a superset of the rows whose exact score can reach the k-th) is re-scored exactly in
+// place, the best k are selected; the result is the exact top-k.  A pool that overflowed leaves the query flagged.
+__global__ void __launch_bounds__(kSel2Threads) pool_rescore_kernel(const PoolParams p) {
+    __shared__ unsigned long long sel[kSel2Max];
+    __shared__ int hist[256];
+    __shared__ float red[32];
+    __shared__ int s_nsel;
+    __shared__ unsigned long long s_prefix;
+    __shared__ int s_remaining, s_ties;
+    extern __shared__ float pqs[];               // [dim]
+    const int j = blockIdx.x;
+    if (j >= *p.nsel) return;
+    const int qg = p.qmap[j];
+    const int tid = threadIdx.x;
+    if (j >= p.max_slots) return;                // never scanned: stays flagged
+    const int n = p.pool_cnt[j];
+    if (n > p.pool_cap) return;                  // overflow: stays flagged, the exact scan answers
+    float part = 0.f;
+    if (tid < 256) {
+        for (int d = tid; d < p.dim; d += 256) {
+            const float v = p.q[static_cast<size_t>(qg) * p.dim + d];
+            pqs[d] = v;
+            part = fmaf(v, v, part);
+        }
+    }
+    const float qnorm = sqrtf(block_sum(part, red));
+    if (tid == 0) s_nsel = 0;
+    unsigned long long* pool = p.pool + static_cast<size_t>(j) * p.pool_cap;
+    for (int c0 = 0; c0 < n; c0 += kSel2Threads / 4) {
+        const int c = c0 + (tid >> 2);
+        const bool live = c < n;
+        const uint32_t row = live ? key_row(pool[c]) : 0u;
+        const float v = exact_metric_quad(pqs, p.x + static_cast<long long>(row) * p.dim, p.dim, p.metric, qnorm);
+        __syncwarp();
+        if (live && (tid & 3) == 0) pool[c] = make_key(metric_to_rank(v, p.metric), row);
+    }
+    __syncthreads();
+    auto load_key = [&](long long idx) -> unsigned long long { return pool[idx]; };
+    const unsigned long long T = block_radix_select(load_key, n, p.k, hist, &s_prefix, &s_remaining, &s_ties);
+    __syncthreads();
+    for (int i = tid; i < n; i += blockDim.x) {
+        const unsigned long long key = pool[i];
+        if (key >= T) { const int pos = atomicAdd(&s_nsel, 1); if (pos < kSel2Max) sel[pos] = key; }
+    }
+    __syncthreads();
+    const int ncand = min(s_nsel, p.k);
+    int m2 = 32;
+    while (m2 < min(s_nsel, kSel2Max)) m2 <<= 1;
+    for (int i = min(s_nsel, kSel2Max) + tid; i < m2; i += blockDim.x) sel[i] = 0ull;
+    block_bitonic_desc(sel, m2);
+    const float missing = p.metric == RMU_METRIC_L2 ? INFINITY : -INFINITY;
+    for (int jj = tid; jj < p.k; jj += blockDim.x) {
+        float sc = missing;
+        long long id = -1;
+        if (jj < ncand) {
+            const float rk = key_score(sel[jj]);
+            sc = p.metric == RMU_METRIC_L2 ? -rk : rk;
+            id = p.id_offset + key_row(sel[jj]);
+        }
+        p.out_scores[static_cast<long long>(qg) * p.k + jj] = sc;
+        p.out_ids[static_cast<long long>(qg) * p.k + jj] = id;
+    }
+    if (tid == 0) p.flags[qg] = 0;               // answered exactly
 }

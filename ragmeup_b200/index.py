@@ -29,7 +29,7 @@ class FlatIndex:
         self._h = C.c_void_p()
         with torch.cuda.device(self.device):
             _lib.check(_lib.lib().rmu_index_create(self.dim, METRICS[metric], C.byref(self._h)), "rmu_index_create")
-        self.last_stats = (0, 0)
+        self.last_stats = (0, 0, 0)
 
     def __del__(self):
         h = getattr(self, "_h", None)
@@ -125,7 +125,7 @@ class FlatIndex:
                                                    C.cast(stats, C.c_void_p) if want_stats else None,
                                                    _lib.stream_ptr()), "rmu_index_search")
         if want_stats:
-            self.last_stats = (int(stats[0]), int(stats[1]))
+            self.last_stats = (int(stats[0]), int(stats[1]), int(stats[2]))
         return scores, ids
 
     def search_host(self, queries: np.ndarray, k: int, id_offset: int = 0, mode: int = MODE_AUTO):

@@ -107,9 +107,10 @@ def test_wide_vectors_on_the_tensor_scan(cuda, metric, dim, n, nq, k):
     _check_topk_fp64(s1, i1, q.cpu().numpy(), x.cpu().numpy(), k, metric)
 
 
-def test_certificate_falls_back_on_near_duplicates(cuda):
-    """more near-ties than the coarse pass keeps: the certificate must fail and the exact fp32 scan must
-    answer (bit-identical to MODE_EXACT; valid top-k in float64 up to fp32 near-ties)"""
+def test_certificate_failure_is_answered_by_the_second_pass(cuda):
+    """more near-ties than the coarse pass re-scores: the certificate must fail; the second tensor pass (every row whose
+    coarse key can reach the k-th exact score, re-scored exactly) must answer without the CUDA-core scan, bit-identical to
+    MODE_EXACT and a valid top-k in float64 up to fp32 near-ties"""
     from ragmeup_b200.index import MODE_AUTO, MODE_EXACT, MODE_TENSOR_NOFALLBACK
     g = torch.Generator(device="cuda").manual_seed(3)
     base = torch.nn.functional.normalize(torch.randn(1, 384, device="cuda", generator=g), dim=1)
@@ -117,13 +118,45 @@ def test_certificate_falls_back_on_near_duplicates(cuda):
     x[1000:1400] = torch.nn.functional.normalize(base + 1e-4 * torch.randn(400, 384, device="cuda", generator=g), dim=1)
     ix = _idx(cuda, x, "ip")
     s, i = ix.search(base, 10, mode=MODE_AUTO, want_stats=True)
-    assert ix.last_stats[0] == 1                      # flagged -> re-run on the exact path
+    assert ix.last_stats[0] == 1                      # flagged by the certificate ...
+    assert ix.last_stats[2] == 0                      # ... and answered by the second pass, not by the exact scan
     s0, i0 = ix.search(base, 10, mode=MODE_EXACT)
     assert (i == i0).all() and (s == s0).all()
     assert ((i >= 1000) & (i < 1400)).all()
     _check_topk_fp64(s, i, base.cpu().numpy(), x.cpu().numpy(), 10, "ip")
     ix.search(base, 10, mode=MODE_TENSOR_NOFALLBACK, want_stats=True)
     assert ix.last_stats[0] == 1
+
+
+@pytest.mark.parametrize("metric", ["ip", "cosine", "l2"])
+def test_second_pass_on_clustered_corpus_and_pool_overflow(cuda, metric):
+    """a clustered corpus (every query sits in a cluster of ~600 rows within 1e-3 of each other): all queries flagged,
+    all answered by the second pass, results bit-identical to the exact scan; a cluster larger than the pool (20 000
+    copies of one row) overflows it and falls through to the exact scan, still exact"""
+    from ragmeup_b200.index import MODE_AUTO, MODE_EXACT
+    g = torch.Generator(device="cuda").manual_seed(17)
+    n, d, nq = 60_000, 384, 33
+    centers = torch.nn.functional.normalize(torch.randn(100, d, device="cuda", generator=g), dim=1)
+    cid = torch.randint(0, 100, (n,), device="cuda", generator=g)
+    x = torch.nn.functional.normalize(centers[cid] + 2e-4 * torch.randn(n, d, device="cuda", generator=g), dim=1)
+    if metric == "l2":
+        x = x * (1.0 + 0.1 * torch.rand(n, 1, device="cuda", generator=g))
+    q = torch.nn.functional.normalize(centers[:nq] + 2e-4 * torch.randn(nq, d, device="cuda", generator=g), dim=1)
+    ix = _idx(cuda, x, metric)
+    s, i = ix.search(q, 20, mode=MODE_AUTO, want_stats=True)
+    flagged, _, to_exact = ix.last_stats
+    s0, i0 = ix.search(q, 20, mode=MODE_EXACT)
+    assert (i == i0).all() and (s == s0).all()
+    if metric != "l2":
+        assert flagged == nq and to_exact == 0
+    big = torch.nn.functional.normalize(torch.randn(1, d, device="cuda", generator=g), dim=1)
+    xb = torch.cat([x, big.repeat(20_000, 1)])
+    ixb = _idx(cuda, xb, "ip")
+    s, i = ixb.search(big, 10, mode=MODE_AUTO, want_stats=True)
+    assert ixb.last_stats[0] == 1 and ixb.last_stats[2] == 1          # pool overflow -> the exact scan
+    s0, i0 = ixb.search(big, 10, mode=MODE_EXACT)
+    assert (i == i0).all() and (s == s0).all()
+    assert (i.cpu().numpy()[0] == np.arange(n, n + 10)).all()         # 20 000 exact ties: the lowest rows win
 
 
 def test_empty_add_growth_offsets_and_host_api(cuda):
