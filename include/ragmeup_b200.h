@@ -51,7 +51,7 @@ uint64_t rmu_launch_count(void);
 
 /* per-kernel-class device timing (CUDA events on the launching stream; used by bench.py for the
  * roofline objects).  classes: 0 scan, 1 finalize, 2 exact scan, 3 merge, 4 gemm, 5 attention,
- * 6 layernorm, 7 embedding, 8 pool/head, 9 misc, 10 unused (round-1 lead pass).  rmu_profile_read synchronises the recorded events. */
+ * 6 layernorm, 7 embedding, 8 pool/head, 9 misc, 10 second-pass scan launches (queries whose certificate failed; exit at once when there are none).  rmu_profile_read synchronises the recorded events. */
 void rmu_profile_enable(int on);
 void rmu_profile_reset(void);
 int rmu_profile_read(int cls, double* total_ms, int64_t* launches);

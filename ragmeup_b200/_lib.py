@@ -136,7 +136,7 @@ def stream_ptr(torch_stream=None) -> int:
 
 
 PROF_CLASSES = ["scan", "finalize", "exact", "merge", "gemm", "attention", "layernorm", "embedding", "pool_head", "misc",
-                "scan_lead"]
+                "scan_pass2"]
 
 
 def profile_enable(on: bool) -> None:

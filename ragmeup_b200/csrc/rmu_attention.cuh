@@ -156,7 +156,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tq_hi, const __grid_cons
 
     if (warp == 0) {
         // =========================== TMA producer ===========================
-        if (lane == 0) {
+        if (elect_one()) {
             int i = 0;
             for (int u = blockIdx.x; u < nunits; u += gridDim.x) {
                 AtcUnit un;
@@ -183,7 +183,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tq_hi, const __grid_cons
         }
     } else if (warp == 1) {
         // =========================== S = Q K^T issuer ===========================
-        if (lane == 0) {
+        if (elect_one()) {
             int i = 0;
             for (int u = blockIdx.x; u < nunits; u += gridDim.x) {
                 AtcUnit un;
@@ -212,7 +212,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tq_hi, const __grid_cons
         }
     } else if (warp == 2) {
         // =========================== O = P V issuer ===========================
-        if (lane == 0) {
+        if (elect_one()) {
             int i = 0;
             uint32_t ppar[2] = {0u, 0u};                         // bit c = parity the next wait on p_full[g][c] uses
             for (int u = blockIdx.x; u < nunits; u += gridDim.x) {
@@ -376,9 +376,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tq_hi, const __grid_cons
 // (13.2 B/clk/SM with the 64-byte rows of one d_h = 32 head; 25.6 B/clk/SM in the scan's 128-byte rows), and the kernel
 // spent its 367 us per layer call fetching 19.7 M such rows (K and V twice per sequence, once per query-row tile; 192 rows
 // for 147 keys) while tensor pipe, MUFU and issue slots idled.  Here
-//   * a work item is (sequence, PAIR of adjacent heads): Q, K and V boxes are 128 bytes wide (both heads), SWIZZLE_128B;
-//     the two heads are the two in-flight units (TMEM buffer g = head 2*hp + g); their operands are the same shared-
-//     memory tiles, addressed 64 bytes apart inside the swizzled rows;
+//   * the QKV GEMM writes every head's q / k / v row as ONE 128-byte line [32 hi halves | 32 lo halves] (GemmParams::
+//     interleave32), so all TMA boxes are 128 bytes wide (SWIZZLE_128B) and the hi / lo parts of an operand are the two
+//     64-byte halves of its swizzled rows; a work item is (sequence, PAIR of adjacent heads), the two heads are the two
+//     in-flight units (TMEM buffer g = head 2*hp + g);
+//   * O = P V takes TWO MMAs per 16 keys instead of three: P_hi x [V_hi | V_lo] is one N = 64 MMA (V's row IS hi | lo),
+//     P_lo x V_hi one N = 32 MMA -- an N = 32 MMA costs the tensor pipe ~110 cycles for 16 cycles of math (its 4 KB A tile
+//     streams from TMEM), so the count of MMAs, not their width, is what a unit pays for;
 //   * K and V of a work item are loaded once and serve all its query-row tiles; boxes are 32 rows, so 147 keys fetch
 //     160 rows, and a 19-row last tile fetches 32 Q rows;
 // i.e. 480 box rows per (sequence, head) instead of 2048.  Roles: warp 0 TMA, warp 1 S = Q K^T issuer (both heads),
@@ -387,7 +391,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tq_hi, const __grid_cons
 constexpr int kApThreads = 640;
 constexpr int kApMaxKeys = 160;                // keys (16-aligned) + three O accumulators of 32 columns = 256 TMEM columns
 constexpr int kApRowB = 128;                   // operand row: two heads x 32 halves
-constexpr int kApQSlot = 2 * kAtcRows * kApRowB;   // Q_hi, Q_lo of one query-row tile
+constexpr int kApQSlot = 2 * kAtcRows * kApRowB;   // the Q tiles (hi | lo rows) of both heads
 constexpr int kApStateBytes = 512 + 4 * 128 * 4;
 
 struct ApParams {
@@ -395,20 +399,31 @@ struct ApParams {
     int B, heads, H;
     int kp;                 // rows per K / V plane of a slot: max_seqlen rounded up to 32 (<= kApMaxKeys)
     __half* ctx_hi; __half* ctx_lo;
+    unsigned long long* trace;      // study (RMU_ATTN_TRACE=1): [0] = entry count, then (event << 48 | arg << 32 | clock) of CTA 0
 };
 
+// study: one store per event into the calling role's own lane of the buffer (no atomics: an atomic's round trip would
+// stall the single-thread issuers the trace is meant to observe)
+constexpr int kApTraceRoles = 8, kApTraceLen = 1024;
+__device__ __forceinline__ void ap_trace(const ApParams& p, int role, uint32_t& tn, unsigned ev, unsigned arg) {
+    if (p.trace != nullptr && blockIdx.x == 0 && tn < static_cast<uint32_t>(kApTraceLen))
+        p.trace[role * kApTraceLen + tn++] = (static_cast<unsigned long long>(ev) << 48) | (static_cast<unsigned long long>(arg & 0xFFFF) << 32) |
+                                             (static_cast<unsigned long long>(clock64()) & 0xFFFFFFFFull);
+}
+
 __global__ void __launch_bounds__(kApThreads, 1)
-attention_pair_kernel(const __grid_constant__ CUtensorMap t_hi, const __grid_constant__ CUtensorMap t_lo, const ApParams p) {
+attention_pair_kernel(const __grid_constant__ CUtensorMap t_qkv, const ApParams p) {
     constexpr int DH = 32;
     constexpr uint32_t LAYOUT = 2u;                        // SWIZZLE_128B
     constexpr uint32_t SBO = 8 * kApRowB;
     constexpr int OCOL = kAtcBufCols - 3 * DH;             // 160
-    constexpr uint32_t IDESC_O = umma_idesc(0 /*f16*/, kAtcRows, DH) | (1u << 16);   // B = V, MN-major
+    constexpr uint32_t IDESC_O64 = umma_idesc(0 /*f16*/, kAtcRows, 2 * DH) | (1u << 16);   // B = [V_hi | V_lo], MN-major
+    constexpr uint32_t IDESC_O32 = umma_idesc(0 /*f16*/, kAtcRows, DH) | (1u << 16);       // B = V_hi
 
     extern __shared__ __align__(1024) uint8_t ap_smem_raw[];     // two K / V slots + two Q slots use all 227 KB at 160 keys:
     uint8_t* smem = ap_smem_raw;                                  // no room for an alignment pad, the declaration must deliver it
     if ((smem_u32(ap_smem_raw) & 1023u) != 0u) __trap();
-    const int kvplane = p.kp * kApRowB;                    // one of K_hi, K_lo, V_hi, V_lo
+    const int kvplane = p.kp * kApRowB;                    // K (or V) of one head: kp rows of [hi | lo]
     const int kvslot = 4 * kvplane;
     uint8_t* kvring = smem;                                // 2 slots
     uint8_t* qring = smem + 2 * kvslot;                    // 2 slots
@@ -428,6 +443,7 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap t_hi, const __grid_con
     const unsigned lane = lane_id();
     const int hpairs = p.heads >> 1;
     const int nwork = p.B * hpairs;
+    uint32_t tn = 0;                                       // trace entries this thread has written
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < 2; ++i) {
@@ -436,7 +452,7 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap t_hi, const __grid_con
             for (int c = 0; c < kAtcMaxChunks; ++c) mbar_init(&p_full[i * kAtcMaxChunks + c], 1);
         }
         fence_mbar_init();
-        prefetch_tmap(&t_hi); prefetch_tmap(&t_lo);
+        prefetch_tmap(&t_qkv);
     }
     if (warp == 1) tmem_alloc<512>(tmem_slot);
     tc_fence_before();
@@ -446,33 +462,35 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap t_hi, const __grid_con
 
     if (warp == 0) {
         // =========================== TMA producer ===========================
-        if (lane == 0) {
+        if (elect_one()) {
             int kvi = 0, qi = 0;
             for (int w = blockIdx.x; w < nwork; w += gridDim.x) {
                 const int b = w / hpairs, hp = w % hpairs;
                 const int t0 = __ldg(p.cu + b), S = __ldg(p.cu + b + 1) - t0;
-                const int col = hp * 64;
+                const int col = hp * 128;                        // interleaved layout: a head is 64 halves, a pair 128
                 const int kvs = kvi & 1;
                 mbar_wait(&kv_empty[kvs], ((kvi >> 1) & 1) ^ 1);
                 const int nkb = (S + 31) >> 5;
                 uint8_t* kb0 = kvring + kvs * kvslot;
+                ap_trace(p, 0, tn, 1, kvi);
                 mbar_arrive_expect_tx(&kv_full[kvs], static_cast<uint32_t>(4 * nkb * 32 * kApRowB));
                 for (int kb = 0; kb < nkb; ++kb) {
                     uint8_t* d = kb0 + kb * 32 * kApRowB;
-                    tma_load_2d(d, &t_hi, p.H + col, t0 + kb * 32, &kv_full[kvs], kEvictNormal);
-                    tma_load_2d(d + kvplane, &t_lo, p.H + col, t0 + kb * 32, &kv_full[kvs], kEvictNormal);
-                    tma_load_2d(d + 2 * kvplane, &t_hi, 2 * p.H + col, t0 + kb * 32, &kv_full[kvs], kEvictNormal);
-                    tma_load_2d(d + 3 * kvplane, &t_lo, 2 * p.H + col, t0 + kb * 32, &kv_full[kvs], kEvictNormal);
+                    tma_load_2d(d, &t_qkv, 2 * p.H + col, t0 + kb * 32, &kv_full[kvs], kEvictNormal);                  // K, head 0
+                    tma_load_2d(d + kvplane, &t_qkv, 2 * p.H + col + 64, t0 + kb * 32, &kv_full[kvs], kEvictNormal);   // K, head 1
+                    tma_load_2d(d + 2 * kvplane, &t_qkv, 4 * p.H + col, t0 + kb * 32, &kv_full[kvs], kEvictNormal);    // V, head 0
+                    tma_load_2d(d + 3 * kvplane, &t_qkv, 4 * p.H + col + 64, t0 + kb * 32, &kv_full[kvs], kEvictNormal);
                 }
                 for (int r0 = 0; r0 < S; r0 += kAtcRows, ++qi) {
                     const int qs = qi & 1;
                     mbar_wait(&q_empty[qs], ((qi >> 1) & 1) ^ 1);
                     const int nqb = (min(kAtcRows, S - r0) + 31) >> 5;
                     uint8_t* q0 = qring + qs * kApQSlot;
+                    ap_trace(p, 0, tn, 2, qi);
                     mbar_arrive_expect_tx(&q_full[qs], static_cast<uint32_t>(2 * nqb * 32 * kApRowB));
                     for (int qb = 0; qb < nqb; ++qb) {
-                        tma_load_2d(q0 + qb * 32 * kApRowB, &t_hi, col, t0 + r0 + qb * 32, &q_full[qs], kEvictNormal);
-                        tma_load_2d(q0 + kAtcRows * kApRowB + qb * 32 * kApRowB, &t_lo, col, t0 + r0 + qb * 32, &q_full[qs], kEvictNormal);
+                        tma_load_2d(q0 + qb * 32 * kApRowB, &t_qkv, col, t0 + r0 + qb * 32, &q_full[qs], kEvictNormal);
+                        tma_load_2d(q0 + kAtcRows * kApRowB + qb * 32 * kApRowB, &t_qkv, col + 64, t0 + r0 + qb * 32, &q_full[qs], kEvictNormal);
                     }
                 }
                 ++kvi;
@@ -480,7 +498,7 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap t_hi, const __grid_con
         }
     } else if (warp == 1) {
         // =========================== S = Q K^T issuer, both heads ===========================
-        if (lane == 0) {
+        if (elect_one()) {
             int kvi = 0, qi = 0;
             uint32_t cnt = 0;                                    // tiles issued so far (the same for both heads)
             for (int w = blockIdx.x; w < nwork; w += gridDim.x) {
@@ -488,26 +506,30 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap t_hi, const __grid_con
                 const int S = __ldg(p.cu + b + 1) - __ldg(p.cu + b);
                 const int kvs = kvi & 1;
                 mbar_wait(&kv_full[kvs], (kvi >> 1) & 1);
-                const uint32_t kh = smem_u32(kvring + kvs * kvslot), kl = kh + kvplane;
+                const uint32_t kbase = smem_u32(kvring + kvs * kvslot);
                 const uint32_t idesc_s = umma_idesc(0 /*f16*/, kAtcRows, ((S + 15) >> 4) << 4);
                 for (int r0 = 0; r0 < S; r0 += kAtcRows, ++qi, ++cnt) {
                     const int qs = qi & 1;
                     mbar_wait(&q_full[qs], (qi >> 1) & 1);
-                    const uint32_t qh = smem_u32(qring + qs * kApQSlot), ql = qh + kAtcRows * kApRowB;
+                    ap_trace(p, 1, tn, 3, cnt);
+                    const uint32_t qbase = smem_u32(qring + qs * kApQSlot);
 #pragma unroll
                     for (int g = 0; g < 2; ++g) {
                         mbar_wait(&s_free[g], (cnt & 1) ^ 1);    // P V of this head's previous tile no longer reads the buffer
                         tc_fence_after();
+                        ap_trace(p, 1, tn, 4 + g, cnt);
                         const uint32_t d_addr = tmem_base + g * kAtcBufCols;
+                        const uint32_t qg = qbase + g * kAtcRows * kApRowB, kg = kbase + g * kvplane;   // rows = [hi 64 B | lo 64 B]
 #pragma unroll
                         for (int term = 0; term < 3; ++term) {
-                            const uint32_t a = (term == 1 ? ql : qh) + g * 64, bb = (term == 2 ? kl : kh) + g * 64;
+                            const uint32_t a = qg + (term == 1 ? 64 : 0), bb = kg + (term == 2 ? 64 : 0);
 #pragma unroll
                             for (int k = 0; k < 2; ++k)
                                 mma_f16_ss(d_addr, atc_desc(a + k * 32, SBO, LAYOUT), atc_desc(bb + k * 32, SBO, LAYOUT), idesc_s,
                                            (term | k) != 0 ? 1u : 0u);
                         }
                         tc_commit(&s_full[g]);
+                        ap_trace(p, 1, tn, 6 + g, cnt);
                     }
                     tc_commit(&q_empty[qs]);                     // the Q tile has been read by both heads' MMAs
                 }
@@ -516,7 +538,7 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap t_hi, const __grid_con
         }
     } else if (warp < 4) {
         // =========================== O = P V issuer of head g ===========================
-        if (lane == 0) {
+        if (elect_one()) {
             const int g = warp - 2;
             int kvi = 0;
             uint32_t ppar = 0u;                                  // bit c = parity the next wait on p_full[g][c] uses
@@ -524,23 +546,24 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap t_hi, const __grid_con
                 const int b = w / hpairs;
                 const int S = __ldg(p.cu + b + 1) - __ldg(p.cu + b);
                 const int kvs = kvi & 1;
-                const uint32_t vh = smem_u32(kvring + kvs * kvslot + 2 * kvplane) + g * 64, vl = vh + kvplane;
+                const uint32_t vg = smem_u32(kvring + kvs * kvslot + (2 + g) * kvplane);      // V rows of this head: [hi | lo]
                 const uint32_t pbase = tmem_base + g * kAtcBufCols;
-                const uint32_t d0 = pbase + OCOL, d1 = d0 + DH, d2 = d0 + 2 * DH;
+                const uint32_t d0 = pbase + OCOL, d1 = d0 + 2 * DH;   // [P_hi V_hi | P_hi V_lo] (64 columns), P_lo V_hi (32)
                 const int nk16 = (S + 15) >> 4, nchunk = (S + 31) >> 5;
                 for (int r0 = 0; r0 < S; r0 += kAtcRows) {
                     for (int c = 0; c < nchunk; ++c) {
                         mbar_wait(&p_full[g * kAtcMaxChunks + c], (ppar >> c) & 1u);
                         ppar ^= 1u << c;
                         tc_fence_after();
+                        ap_trace(p, 2 + g, tn, 10 + g, c);
                         for (int j16 = 2 * c; j16 < min(2 * c + 2, nk16); ++j16) {
                             const uint32_t a_hi = pbase + 32 * c + 8 * (j16 & 1), a_lo = a_hi + 16;
-                            const uint64_t bh = atc_desc(vh + j16 * 16 * kApRowB, SBO, LAYOUT), bl = atc_desc(vl + j16 * 16 * kApRowB, SBO, LAYOUT);
+                            const uint64_t bv = atc_desc(vg + j16 * 16 * kApRowB, SBO, LAYOUT);
                             const uint32_t acc = j16 != 0 ? 1u : 0u;
-                            mma_f16_ts(d0, a_hi, bh, IDESC_O, acc);
-                            mma_f16_ts(d1, a_lo, bh, IDESC_O, acc);
-                            mma_f16_ts(d2, a_hi, bl, IDESC_O, acc);
+                            mma_f16_ts(d0, a_hi, bv, IDESC_O64, acc);
+                            mma_f16_ts(d1, a_lo, bv, IDESC_O32, acc);
                         }
+                        ap_trace(p, 2 + g, tn, 12 + g, c);
                     }
                     tc_commit(&o_full[g]);
                     tc_commit(&s_free[g]);
@@ -568,6 +591,7 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap t_hi, const __grid_con
                 const bool warp_live = r0 + quad * 32 < S;
                 mbar_wait(&s_full[g], cnt & 1);
                 tc_fence_after();
+                if (htid == 0) ap_trace(p, 4 + g + 2 * half, tn, 20 + g, cnt);
                 float m = -INFINITY;
                 if (warp_live) {
                     for (int c = half; c < nchunk; c += 2) {
@@ -587,6 +611,7 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap t_hi, const __grid_con
                 bar_sync_named(1 + g, 256);
                 m = fmaxf(m, xo[r]);
                 bar_sync_named(1 + g, 256);
+                if (htid == 0) ap_trace(p, 4 + g + 2 * half, tn, 22 + g, cnt);
                 float l = 0.f;
                 for (int c = half; c < nchunk; c += 2) {
                     if (warp_live) {
@@ -611,11 +636,12 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap t_hi, const __grid_con
                     }
                     tc_fence_before();
                     bar_sync_named(3 + g * 2 + half, 128);
-                    if (htid == 0) mbar_arrive(&p_full[g * kAtcMaxChunks + c]);
+                    if (htid == 0) { mbar_arrive(&p_full[g * kAtcMaxChunks + c]); ap_trace(p, 4 + g + 2 * half, tn, 24 + g, c); }
                 }
                 xm[r] = l;
                 mbar_wait(&o_full[g], cnt & 1);
                 tc_fence_after();
+                if (htid == 0) ap_trace(p, 4 + g + 2 * half, tn, 26 + g, cnt);
                 bar_sync_named(1 + g, 256);
                 l += xo[r];
                 const int row = r0 + r;
@@ -644,6 +670,7 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap t_hi, const __grid_con
                         dl[0] = make_uint4(ol[0], ol[1], ol[2], ol[3]); dl[1] = make_uint4(ol[4], ol[5], ol[6], ol[7]);
                     }
                 }
+                if (htid == 0) ap_trace(p, 4 + g + 2 * half, tn, 28 + g, cnt);
                 bar_sync_named(1 + g, 256);
             }
         }

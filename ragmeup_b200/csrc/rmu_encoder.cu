@@ -466,7 +466,8 @@ struct rmu_encoder {
     std::vector<void*> act_allocs;
     SplitOperand X, CTX, X1, FF, QKVP;   // QKVP: q (pre-scaled) | k | v as split planes [T, 3H]
     CUtensorMap att_q_hi{}, att_q_lo{}, att_k_hi{}, att_k_lo{};   // tcgen05 attention: boxes {d_h, 128 rows} / {d_h, 64 rows} of QKVP
-    CUtensorMap att_p_hi{}, att_p_lo{};                           // head-pair attention (d_h = 32): boxes {64 halves, 32 rows}
+    __half* QKVI = nullptr;                                       // [T, 6H]: q | k | v with every head's hi and lo halves interleaved
+    CUtensorMap att_qkvi{};                                       // head-pair attention (d_h = 32): boxes {64 halves, 32 rows} of QKVI
     float* PRE = nullptr;                 // fp32 pre-LayerNorm rows (hidden sizes the fused GEMM+LN kernel does not cover)
     // staging of the *_host entry points: owned by host_mu alone (NOT part of the activation workspace, which a
     // concurrent device-pointer caller may free and re-allocate under mu)
@@ -549,8 +550,11 @@ static int ensure_tokens(rmu_encoder* e, int T, int B) {
         if (rc == RMU_OK) rc = make_tmap_2d(&e->att_q_lo, e->QKVP.lo, cap, 3 * H, pitch, DH, kAtcRows, 2);
         if (rc == RMU_OK) rc = make_tmap_2d(&e->att_k_hi, e->QKVP.hi, cap, 3 * H, pitch, DH, 64, 2);
         if (rc == RMU_OK) rc = make_tmap_2d(&e->att_k_lo, e->QKVP.lo, cap, 3 * H, pitch, DH, 64, 2);
-        if (rc == RMU_OK && DH == 32) rc = make_tmap_2d(&e->att_p_hi, e->QKVP.hi, cap, 3 * H, pitch, 64, 32, 2);
-        if (rc == RMU_OK && DH == 32) rc = make_tmap_2d(&e->att_p_lo, e->QKVP.lo, cap, 3 * H, pitch, 64, 32, 2);
+        if (rc == RMU_OK && DH == 32) {
+            rc = dev_alloc(e->act_allocs, &e->QKVI, static_cast<size_t>(cap) * 6 * H);
+            if (rc == RMU_OK) RMU_CUDA(cudaMemset(e->QKVI, 0, static_cast<size_t>(cap) * 6 * H * sizeof(__half)));
+            if (rc == RMU_OK) rc = make_tmap_2d(&e->att_qkvi, e->QKVI, cap, 6 * H, 2 * pitch, 64, 32, 2);
+        }
     }
     if (rc == RMU_OK) rc = dev_alloc(e->act_allocs, &e->PRE, static_cast<size_t>(cap) * H);
     if (rc != RMU_OK) { free_acts(e); return rc; }
@@ -586,6 +590,9 @@ static int run_encoder(rmu_encoder* e, const int32_t* ids, const int32_t* type_i
         // q (scaled by 1/sqrt(dh)), k, v leave the GEMM as split fp16 planes: attention does no conversions
         // (the softmax runs in base 2: q also carries log2(e))
         g.out_hi = e->QKVP.hi; g.out_lo = e->QKVP.lo; g.qcols = H; g.qscale = scale * 1.4426950408889634f;
+        // the head-pair attention kernel reads q / k / v with hi and lo of a head interleaved in one 128-byte line
+        const bool pair_attn = attn_mode == 0 && DH == 32 && c.heads % 2 == 0 && max_seqlen <= kApMaxKeys;
+        if (pair_attn) { g.out_hi = e->QKVI; g.out_lo = nullptr; g.interleave32 = 1; }
         rc = launch_gemm(GEMM_BIAS_SPLIT_QSCALE, e->X, L.Wqkv, g, e->sms, st);
         if (rc != RMU_OK) return rc;
         {
@@ -595,7 +602,7 @@ static int run_encoder(rmu_encoder* e, const int32_t* ids, const int32_t* type_i
             const int kp = (max_seqlen + 63) / 64 * 64;
             const int slot_bytes = 2 * kAtcRows * DH * 2 + 4 * kp * DH * 2;
             const int nslots = std::min(kAtcMaxSlots, (227 * 1024 - 1024 - kAtcStateBytes) / slot_bytes);
-            if (attn_mode == 0 && DH == 32 && c.heads % 2 == 0 && max_seqlen <= kApMaxKeys) {
+            if (pair_attn) {
                 // head-pair kernel: 128-byte operand rows, K / V shared by the query-row tiles of a sequence
                 ApParams ap{};
                 ap.cu = cu; ap.B = B; ap.heads = c.heads; ap.H = H; ap.kp = (max_seqlen + 31) / 32 * 32;
@@ -605,7 +612,26 @@ static int run_encoder(rmu_encoder* e, const int32_t* ids, const int32_t* type_i
                 const long long nwork = static_cast<long long>(B) * (c.heads / 2);
                 const unsigned grid = static_cast<unsigned>(std::min<long long>(e->sms, nwork));
                 RMU_CUDA(cudaFuncSetAttribute(attention_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-                attention_pair_kernel<<<grid, kApThreads, smem, st>>>(e->att_p_hi, e->att_p_lo, ap);
+                static const int att_trace = [] { const char* e = getenv("RMU_ATTN_TRACE"); return e ? atoi(e) : 0; }();
+                static unsigned long long* trace_buf = nullptr;
+                constexpr size_t trace_n = static_cast<size_t>(kApTraceRoles) * kApTraceLen;
+                if (att_trace && l == 1) {                           // study: event timeline of CTA 0, second layer of a call
+                    if (!trace_buf) cudaMalloc(reinterpret_cast<void**>(&trace_buf), trace_n * sizeof(unsigned long long));
+                    cudaMemsetAsync(trace_buf, 0, trace_n * sizeof(unsigned long long), st);
+                    ap.trace = trace_buf;
+                }
+                attention_pair_kernel<<<grid, kApThreads, smem, st>>>(e->att_qkvi, ap);
+                if (att_trace && l == 1) {
+                    std::vector<unsigned long long> h(trace_n);
+                    cudaMemcpyAsync(h.data(), trace_buf, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st);
+                    cudaStreamSynchronize(st);
+                    FILE* f = fopen("gpurun_out/att_trace.txt", "w");
+                    if (f) {
+                        for (size_t i = 0; i < trace_n; ++i)
+                            if (h[i] != 0) fprintf(f, "%llu %llu %llu\n", h[i] >> 48, (h[i] >> 32) & 0xFFFF, h[i] & 0xFFFFFFFFull);
+                        fclose(f);
+                    }
+                }
             } else if ((attn_mode == 0 || attn_mode == 1) && max_seqlen <= kAtcBufCols - DH && nslots >= 2) {
                 AtcParams ap{};
                 ap.cu = cu; ap.B = B; ap.heads = c.heads; ap.H = H; ap.row_tiles = (max_seqlen + kAtcRows - 1) / kAtcRows;

@@ -40,6 +40,9 @@ struct GemmParams {
     __half* out_hi; __half* out_lo;       // [M, N]
     const __half* res_hi; const __half* res_lo;  // [M, N]
     int qcols; float qscale;              // GEMM_BIAS_SPLIT_QSCALE
+    int interleave32;                     // GEMM_BIAS_SPLIT_QSCALE: out_hi is ONE buffer [M, 2N] where every 32-column group
+                                          // (a d_h = 32 head) is stored as 32 hi halves followed by its 32 lo halves: a head's
+                                          // q / k / v row is one 128-byte line (what attention_pair_kernel's TMA boxes fetch)
     int l2_prefetch;                      // RMU_GEMM_L2PF=1: prefetch the next row block's A boxes into L2 one tile ahead
 };
 
@@ -115,7 +118,7 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tAh, const __grid_constant
     const int tiles = m_blks * n_blks;
 
     if (warp == 0) {
-        if (lane == 0) {
+        if (elect_one()) {
             int slot = 0;
             uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
@@ -142,7 +145,7 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tAh, const __grid_constant
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        if (elect_one()) {
             int slot = 0;
             uint32_t phase = 0;
             int i = 0;
@@ -241,8 +244,14 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tAh, const __grid_constant
                             __half h0, l0, h1, l1;
                             split_f16(a, h0, l0);
                             split_f16(b, h1, l1);
-                            *reinterpret_cast<__half2*>(p.out_hi + o) = __halves2half2(h0, h1);
-                            *reinterpret_cast<__half2*>(p.out_lo + o) = __halves2half2(l0, l1);
+                            if (MODE == GEMM_BIAS_SPLIT_QSCALE && p.interleave32) {
+                                const size_t oi = static_cast<size_t>(grow) * (2 * p.N) + 2 * col0 + cp;   // col0 is a multiple of 32
+                                *reinterpret_cast<__half2*>(p.out_hi + oi) = __halves2half2(h0, h1);
+                                *reinterpret_cast<__half2*>(p.out_hi + oi + 32) = __halves2half2(l0, l1);
+                            } else {
+                                *reinterpret_cast<__half2*>(p.out_hi + o) = __halves2half2(h0, h1);
+                                *reinterpret_cast<__half2*>(p.out_lo + o) = __halves2half2(l0, l1);
+                            }
                         }
                     }
                 }
@@ -355,7 +364,7 @@ gemm_f16x3_ln_kernel(const __grid_constant__ CUtensorMap tAh, const __grid_const
     const int nb = static_cast<int>(rank);        // this CTA's column tile of every row block
 
     if (warp == 0) {
-        if (lane == 0) {
+        if (elect_one()) {
             int slot = 0;
             uint32_t phase = 0;
             for (int mb = cluster_id; mb < m_blks; mb += n_clusters) {
@@ -378,7 +387,7 @@ gemm_f16x3_ln_kernel(const __grid_constant__ CUtensorMap tAh, const __grid_const
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        if (elect_one()) {
             int slot = 0;
             uint32_t phase = 0;
             int i = 0;

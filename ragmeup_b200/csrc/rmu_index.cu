@@ -673,7 +673,7 @@ static int scan_launch_t(const CUtensorMap& tx, const CUtensorMap& tq, const Sca
     at[0].val.clusterDim.x = PAIR ? 2 : 1; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at;
     cfg.numAttrs = 1;
-    ProfScope _ps(PROF_SCAN, st);
+    ProfScope _ps(p.fixed_tau != nullptr ? PROF_SCAN_LEAD : PROF_SCAN, st);   // second-pass launches are timed apart
     RMU_CUDA(cudaLaunchKernelEx(&cfg, kern, tx, tq, p));
     count_launch();
     return RMU_OK;

@@ -183,7 +183,7 @@ scan_rows_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
 
     if (warp == 0) {
         // =========================== TMA producer ===========================
-        if (lane == 0) {
+        if (elect_one()) {
             if (rank == 0) mbar_arrive_expect_tx(qbar, static_cast<uint32_t>(NCTA * KB * QBLK_BYTES));
             for (int kb = 0; kb < KB; ++kb) {
                 if (PAIR) tma_load_2d_pair(qop + kb * QBLK_BYTES, &tmap_q, kb * 32, rank * NQH, qbar, kEvictLast);
@@ -209,7 +209,7 @@ scan_rows_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         }
     } else if (warp == 1) {
         // =========================== MMA issuer (leader only) ===========================
-        if (lane == 0 && rank == 0) {
+        if (rank == 0 && elect_one()) {
             mbar_wait(qbar, 0);                                  // the query operand is resident (both halves)
             tc_fence_after();
             int slot = 0;
