@@ -388,29 +388,53 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tq_hi, const __grid_cons
 // i.e. 480 box rows per (sequence, head) instead of 2048.  Roles: warp 0 TMA, warp 1 S = Q K^T issuer (both heads),
 // warps 2 / 3 the P V issuers of head 0 / 1, then 8 softmax warps per head.
 // =====================================================================================================================
-constexpr int kApThreads = 640;
+constexpr int kApThreads = 768;                // 4 role warps + 4 output warps + 2 heads x 8 softmax warps
 constexpr int kApMaxKeys = 160;                // keys (16-aligned) + three O accumulators of 32 columns = 256 TMEM columns
 constexpr int kApRowB = 128;                   // operand row: two heads x 32 halves
 constexpr int kApQSlot = 2 * kAtcRows * kApRowB;   // the Q tiles (hi | lo rows) of both heads
-constexpr int kApStateBytes = 512 + 4 * 128 * 4;
+constexpr int kApStateBytes = 512 + 4 * 128 * 4;   // barriers | per (head, half, row) exchange slot: row max during pass 1, then the row sum
 
 struct ApParams {
     const int* cu;
     int B, heads, H;
     int kp;                 // rows per K / V plane of a slot: max_seqlen rounded up to 32 (<= kApMaxKeys)
     __half* ctx_hi; __half* ctx_lo;
-    unsigned long long* trace;      // study (RMU_ATTN_TRACE=1): [0] = entry count, then (event << 48 | arg << 32 | clock) of CTA 0
+    unsigned long long* trace;      // study (RMU_ATTN_TRACE=1): per-role event lanes of CTA 0, (event << 48 | arg << 32 | clock)
 };
 
 // study: one store per event into the calling role's own lane of the buffer (no atomics: an atomic's round trip would
 // stall the single-thread issuers the trace is meant to observe)
-constexpr int kApTraceRoles = 8, kApTraceLen = 1024;
+constexpr int kApTraceRoles = 12, kApTraceLen = 1024;
 __device__ __forceinline__ void ap_trace(const ApParams& p, int role, uint32_t& tn, unsigned ev, unsigned arg) {
     if (p.trace != nullptr && blockIdx.x == 0 && tn < static_cast<uint32_t>(kApTraceLen))
         p.trace[role * kApTraceLen + tn++] = (static_cast<unsigned long long>(ev) << 48) | (static_cast<unsigned long long>(arg & 0xFFFF) << 32) |
                                              (static_cast<unsigned long long>(clock64()) & 0xFFFFFFFFull);
 }
 
+// packed fp32 pairs (FADD2 / FFMA2 of sm_100): one issue slot for two lanes' worth of softmax arithmetic
+__device__ __forceinline__ void ap_add2(float& x0, float& x1, float y0, float y1) {
+    asm("{\n\t.reg .b64 a, b;\n\tmov.b64 a, {%0, %1};\n\tmov.b64 b, {%2, %3};\n\tadd.rn.f32x2 a, a, b;\n\tmov.b64 {%0, %1}, a;\n\t}"
+        : "+f"(x0), "+f"(x1) : "f"(y0), "f"(y1));
+}
+__device__ __forceinline__ void ap_sub2(float& x0, float& x1, float y0, float y1) {
+    asm("{\n\t.reg .b64 a, b;\n\tmov.b64 a, {%0, %1};\n\tmov.b64 b, {%2, %3};\n\tsub.rn.f32x2 a, a, b;\n\tmov.b64 {%0, %1}, a;\n\t}"
+        : "+f"(x0), "+f"(x1) : "f"(y0), "f"(y1));
+}
+__device__ __forceinline__ void ap_split_pack(float a, float b, uint32_t& hi, uint32_t& lo) {
+    const __half2 h = __floats2half2_rn(a, b);
+    const float2 hf = __half22float2(h);
+    ap_sub2(a, b, hf.x, hf.y);
+    const __half2 l = __floats2half2_rn(a, b);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
+// The softmax warps of a head run a serial chain per query-row tile (row max, exp + split + write-back, then -- in the
+// first version of this kernel -- the wait for O and its read-out): 7400 cycles per tile of which they computed 45 %,
+// the rest latency, and with TMEM allowing only two heads in flight nothing hid it.  Here the O read-out belongs to four
+// OUTPUT warps (one per TMEM lane quadrant, serving both heads): a softmax warp leaves its row sums in shared memory and
+// goes straight to the next tile's scores, so a head's chain is row max -> exp -> (P V tail -> next S), and the read-out
+// of tile n overlaps the softmax of tile n + 1.
 __global__ void __launch_bounds__(kApThreads, 1)
 attention_pair_kernel(const __grid_constant__ CUtensorMap t_qkv, const ApParams p) {
     constexpr int DH = 32;
@@ -420,7 +444,7 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap t_qkv, const ApParams 
     constexpr uint32_t IDESC_O64 = umma_idesc(0 /*f16*/, kAtcRows, 2 * DH) | (1u << 16);   // B = [V_hi | V_lo], MN-major
     constexpr uint32_t IDESC_O32 = umma_idesc(0 /*f16*/, kAtcRows, DH) | (1u << 16);       // B = V_hi
 
-    extern __shared__ __align__(1024) uint8_t ap_smem_raw[];     // two K / V slots + two Q slots use all 227 KB at 160 keys:
+    extern __shared__ __align__(1024) uint8_t ap_smem_raw[];     // two K / V slots + two Q slots use nearly all 227 KB at 160 keys:
     uint8_t* smem = ap_smem_raw;                                  // no room for an alignment pad, the declaration must deliver it
     if ((smem_u32(ap_smem_raw) & 1023u) != 0u) __trap();
     const int kvplane = p.kp * kApRowB;                    // K (or V) of one head: kp rows of [hi | lo]
@@ -434,10 +458,12 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap t_qkv, const ApParams 
     uint64_t* q_empty = q_full + 2;
     uint64_t* s_full = q_empty + 2;                        // [2] S of head g is complete
     uint64_t* p_full = s_full + 2;                         // [2][8] chunk c of P of head g is written
-    uint64_t* o_full = p_full + 2 * kAtcMaxChunks;         // [2]
-    uint64_t* s_free = o_full + 2;                         // [2] the P V MMAs that read buffer g have completed
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_free + 2);
-    float* xch = reinterpret_cast<float*>(state + 512);    // [2 heads][2 halves][128 rows]
+    uint64_t* o_full = p_full + 2 * kAtcMaxChunks;         // [2] all P V MMAs of head g's tile have completed (output warps)
+    uint64_t* s_free = o_full + 2;                         // [2] the same event, for the S issuer: buffer g may be overwritten
+    uint64_t* l_full = s_free + 2;                         // [2] the 8 softmax warps of head g have left their row sums
+    uint64_t* o_free = l_full + 2;                         // [2] the 4 output warps have read O of head g
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_free + 2);
+    float* xch = reinterpret_cast<float*>(state + 512);    // [2 heads][2 halves][128 rows]: row max (pass 1), then the row sum
 
     const int warp = threadIdx.x >> 5;
     const unsigned lane = lane_id();
@@ -449,7 +475,8 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap t_qkv, const ApParams 
         for (int i = 0; i < 2; ++i) {
             mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 2); mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1);
             mbar_init(&s_full[i], 1); mbar_init(&o_full[i], 1); mbar_init(&s_free[i], 1);
-            for (int c = 0; c < kAtcMaxChunks; ++c) mbar_init(&p_full[i * kAtcMaxChunks + c], 1);
+            mbar_init(&l_full[i], 8); mbar_init(&o_free[i], 4);
+            for (int c = 0; c < kAtcMaxChunks; ++c) mbar_init(&p_full[i * kAtcMaxChunks + c], 4);   // the four warps that own the chunk
         }
         fence_mbar_init();
         prefetch_tmap(&t_qkv);
@@ -541,6 +568,7 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap t_qkv, const ApParams 
         if (elect_one()) {
             const int g = warp - 2;
             int kvi = 0;
+            uint32_t cnt = 0;
             uint32_t ppar = 0u;                                  // bit c = parity the next wait on p_full[g][c] uses
             for (int w = blockIdx.x; w < nwork; w += gridDim.x) {
                 const int b = w / hpairs;
@@ -550,10 +578,11 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap t_qkv, const ApParams 
                 const uint32_t pbase = tmem_base + g * kAtcBufCols;
                 const uint32_t d0 = pbase + OCOL, d1 = d0 + 2 * DH;   // [P_hi V_hi | P_hi V_lo] (64 columns), P_lo V_hi (32)
                 const int nk16 = (S + 15) >> 4, nchunk = (S + 31) >> 5;
-                for (int r0 = 0; r0 < S; r0 += kAtcRows) {
+                for (int r0 = 0; r0 < S; r0 += kAtcRows, ++cnt) {
                     for (int c = 0; c < nchunk; ++c) {
                         mbar_wait(&p_full[g * kAtcMaxChunks + c], (ppar >> c) & 1u);
                         ppar ^= 1u << c;
+                        if (c == 0) mbar_wait(&o_free[g], (cnt & 1) ^ 1);   // the output warps have read the previous tile's O
                         tc_fence_after();
                         ap_trace(p, 2 + g, tn, 10 + g, c);
                         for (int j16 = 2 * c; j16 < min(2 * c + 2, nk16); ++j16) {
@@ -572,20 +601,74 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap t_qkv, const ApParams 
                 ++kvi;
             }
         }
-    } else {
-        // =========================== softmax + output of head g: thread = query row, two warps per row ===========================
-        const int g = (warp - 4) >> 3;
-        const int half = ((warp - 4) >> 2) & 1;                  // which chunks (c & 1) and which half of O's columns
+    } else if (warp < 8) {
+        // =========================== output warps: O / l of both heads -> context planes ===========================
         const int quad = warp & 3;
         const int r = quad * 32 + static_cast<int>(lane);
-        const int htid = ((warp - 4) & 3) * 32 + static_cast<int>(lane);
+        uint32_t cnt = 0;
+        for (int w = blockIdx.x; w < nwork; w += gridDim.x) {
+            const int b = w / hpairs, hp = w % hpairs;
+            const int t0 = __ldg(p.cu + b), S = __ldg(p.cu + b + 1) - t0;
+            for (int r0 = 0; r0 < S; r0 += kAtcRows, ++cnt) {
+                const bool warp_live = r0 + quad * 32 < S;
+                const int row = r0 + r;
+#pragma unroll 1
+                for (int g = 0; g < 2; ++g) {
+                    mbar_wait(&l_full[g], cnt & 1);
+                    const float* lp = xch + g * 2 * kAtcRows;
+                    const float inv = 1.0f / (lp[r] + lp[kAtcRows + r]);
+                    mbar_wait(&o_full[g], cnt & 1);
+                    tc_fence_after();
+                    if (lane == 0) ap_trace(p, 8 + quad, tn, 26 + g, cnt);
+                    const uint32_t ob = tmem_addr(tmem_base, quad * 32, g * kAtcBufCols + OCOL);
+                    uint32_t oh[16], ol[16];
+                    if (warp_live) {
+#pragma unroll
+                        for (int hc = 0; hc < 2; ++hc) {             // 16 output columns at a time
+                            uint32_t o0[16], o1[16], o2[16];
+                            tmem_ld16(ob + hc * 16, o0);
+                            tmem_ld16(ob + DH + hc * 16, o1);
+                            tmem_ld16(ob + 2 * DH + hc * 16, o2);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                const float a = (__uint_as_float(o0[2 * j]) + __uint_as_float(o1[2 * j]) + __uint_as_float(o2[2 * j])) * inv;
+                                const float bq = (__uint_as_float(o0[2 * j + 1]) + __uint_as_float(o1[2 * j + 1]) + __uint_as_float(o2[2 * j + 1])) * inv;
+                                atc_split_pack(a, bq, oh[hc * 8 + j], ol[hc * 8 + j]);
+                            }
+                        }
+                    }
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&o_free[g]);          // O of this head may be overwritten by the next tile's P V
+                    if (warp_live && row < S) {
+                        const size_t off = static_cast<size_t>(t0 + row) * p.H + (2 * hp + g) * DH;
+                        uint4* dh = reinterpret_cast<uint4*>(p.ctx_hi + off);
+                        uint4* dl = reinterpret_cast<uint4*>(p.ctx_lo + off);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            dh[q] = make_uint4(oh[4 * q], oh[4 * q + 1], oh[4 * q + 2], oh[4 * q + 3]);
+                            dl[q] = make_uint4(ol[4 * q], ol[4 * q + 1], ol[4 * q + 2], ol[4 * q + 3]);
+                        }
+                    }
+                    if (lane == 0) ap_trace(p, 8 + quad, tn, 28 + g, cnt);
+                }
+            }
+        }
+    } else {
+        // =========================== softmax of head g: thread = query row, two warps per row ===========================
+        const int g = (warp - 8) >> 3;
+        const int half = ((warp - 8) >> 2) & 1;                  // which chunks (c & 1)
+        const int quad = warp & 3;
+        const int r = quad * 32 + static_cast<int>(lane);
+        const int htid = ((warp - 8) & 3) * 32 + static_cast<int>(lane);
         float* xm = xch + (g * 2 + half) * kAtcRows;
         const float* xo = xch + (g * 2 + (half ^ 1)) * kAtcRows;
         const uint32_t tb = tmem_addr(tmem_base, quad * 32, g * kAtcBufCols);
         uint32_t cnt = 0;
         for (int w = blockIdx.x; w < nwork; w += gridDim.x) {
-            const int b = w / hpairs, hp = w % hpairs;
-            const int t0 = __ldg(p.cu + b), S = __ldg(p.cu + b + 1) - t0;
+            const int b = w / hpairs;
+            const int S = __ldg(p.cu + b + 1) - __ldg(p.cu + b);
             const int nchunk = (S + 31) >> 5;
             for (int r0 = 0; r0 < S; r0 += kAtcRows, ++cnt) {
                 const bool warp_live = r0 + quad * 32 < S;
@@ -594,84 +677,63 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap t_qkv, const ApParams 
                 if (htid == 0) ap_trace(p, 4 + g + 2 * half, tn, 20 + g, cnt);
                 float m = -INFINITY;
                 if (warp_live) {
+                    float m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;   // four independent chains: fmaxf does not reassociate
                     for (int c = half; c < nchunk; c += 2) {
                         uint32_t sv[32];
                         tmem_ld32(tb + c * 32, sv);
                         tmem_ld_wait();
-                        if (c * 32 + 32 <= S) {
+                        if (c * 32 + 32 > S) {
 #pragma unroll
-                            for (int j = 0; j < 32; ++j) m = fmaxf(m, __uint_as_float(sv[j]));
-                        } else {
+                            for (int j = 0; j < 32; ++j) if (c * 32 + j >= S) sv[j] = 0xFF800000u;   // -inf
+                        }
 #pragma unroll
-                            for (int j = 0; j < 32; ++j) m = fmaxf(m, c * 32 + j < S ? __uint_as_float(sv[j]) : -INFINITY);
+                        for (int j = 0; j < 32; j += 4) {
+                            m = fmaxf(m, __uint_as_float(sv[j])); m1 = fmaxf(m1, __uint_as_float(sv[j + 1]));
+                            m2 = fmaxf(m2, __uint_as_float(sv[j + 2])); m3 = fmaxf(m3, __uint_as_float(sv[j + 3]));
                         }
                     }
+                    m = fmaxf(fmaxf(m, m1), fmaxf(m2, m3));
                 }
-                xm[r] = m;
-                bar_sync_named(1 + g, 256);
+                mbar_wait(&o_free[g], (cnt & 1) ^ 1);          // the output warps have taken the previous tile's row sums out of xch
+                xm[r] = m;                                       // (they did so while S of this tile was being computed: no stall)
+                bar_sync_named(1 + g * 4 + quad, 64);            // the two warps that share these 32 rows (same SM sub-partition)
                 m = fmaxf(m, xo[r]);
-                bar_sync_named(1 + g, 256);
+                bar_sync_named(1 + g * 4 + quad, 64);
                 if (htid == 0) ap_trace(p, 4 + g + 2 * half, tn, 22 + g, cnt);
-                float l = 0.f;
+                float l0 = 0.f, l1 = 0.f;
                 for (int c = half; c < nchunk; c += 2) {
                     if (warp_live) {
                         uint32_t sv[32];
                         tmem_ld32(tb + c * 32, sv);
                         tmem_ld_wait();
-                        uint32_t ph[16], pl[16];
-                        const bool tail = c * 32 + 32 > S;
+                        if (c * 32 + 32 > S) {                       // ragged last chunk (warp-uniform): keys past the end weigh nothing
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            float a = atc_exp2(__uint_as_float(sv[2 * j]) - m), bq = atc_exp2(__uint_as_float(sv[2 * j + 1]) - m);
-                            if (tail) {
-                                if (c * 32 + 2 * j >= S) a = 0.f;
-                                if (c * 32 + 2 * j + 1 >= S) bq = 0.f;
-                            }
-                            l += a + bq;
-                            atc_split_pack(a, bq, ph[j], pl[j]);
+                            for (int j = 0; j < 32; ++j) if (c * 32 + j >= S) sv[j] = 0xFF800000u;   // exp2(-inf) = +0
                         }
-                        tmem_st16(tb + c * 32, ph);
-                        tmem_st16(tb + c * 32 + 16, pl);
+#pragma unroll
+                        for (int hc = 0; hc < 2; ++hc) {             // 16 keys at a time: 8 packed hi + 8 packed lo columns
+                            uint32_t ph[8], pl[8];
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                float a = __uint_as_float(sv[hc * 16 + 2 * j]), bq = __uint_as_float(sv[hc * 16 + 2 * j + 1]);
+                                ap_sub2(a, bq, m, m);
+                                a = atc_exp2(a); bq = atc_exp2(bq);
+                                ap_add2(l0, l1, a, bq);
+                                ap_split_pack(a, bq, ph[j], pl[j]);
+                            }
+                            tmem_st8(tb + c * 32 + hc * 8, ph);
+                            tmem_st8(tb + c * 32 + 16 + hc * 8, pl);
+                        }
                         tmem_st_wait();
                     }
                     tc_fence_before();
-                    bar_sync_named(3 + g * 2 + half, 128);
-                    if (htid == 0) { mbar_arrive(&p_full[g * kAtcMaxChunks + c]); ap_trace(p, 4 + g + 2 * half, tn, 24 + g, c); }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&p_full[g * kAtcMaxChunks + c]);     // one arrival per owning warp: no CTA-level barrier
+                    if (htid == 0) ap_trace(p, 4 + g + 2 * half, tn, 24 + g, c);
                 }
-                xm[r] = l;
-                mbar_wait(&o_full[g], cnt & 1);
-                tc_fence_after();
-                if (htid == 0) ap_trace(p, 4 + g + 2 * half, tn, 26 + g, cnt);
-                bar_sync_named(1 + g, 256);
-                l += xo[r];
-                const int row = r0 + r;
-                if (warp_live) {
-                    const float inv = 1.0f / l;
-                    uint32_t o[16];
-                    tmem_ld16(tb + OCOL + half * 16, o);
-                    tmem_ld_wait();
-#pragma unroll 1
-                    for (int t = 1; t < 3; ++t) {
-                        uint32_t o1[16];
-                        tmem_ld16(tb + OCOL + t * DH + half * 16, o1);
-                        tmem_ld_wait();
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) o[j] = __float_as_uint(__uint_as_float(o[j]) + __uint_as_float(o1[j]));
-                    }
-                    if (row < S) {
-                        uint32_t oh[8], ol[8];
-#pragma unroll
-                        for (int j = 0; j < 8; ++j)
-                            atc_split_pack(__uint_as_float(o[2 * j]) * inv, __uint_as_float(o[2 * j + 1]) * inv, oh[j], ol[j]);
-                        const size_t off = static_cast<size_t>(t0 + row) * p.H + (2 * hp + g) * DH + half * 16;
-                        uint4* dh = reinterpret_cast<uint4*>(p.ctx_hi + off);
-                        uint4* dl = reinterpret_cast<uint4*>(p.ctx_lo + off);
-                        dh[0] = make_uint4(oh[0], oh[1], oh[2], oh[3]); dh[1] = make_uint4(oh[4], oh[5], oh[6], oh[7]);
-                        dl[0] = make_uint4(ol[0], ol[1], ol[2], ol[3]); dl[1] = make_uint4(ol[4], ol[5], ol[6], ol[7]);
-                    }
-                }
-                if (htid == 0) ap_trace(p, 4 + g + 2 * half, tn, 28 + g, cnt);
-                bar_sync_named(1 + g, 256);
+                xm[r] = l0 + l1;                                 // row sum for the output warps (every warp of the head is past pass 1)
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&l_full[g]);
             }
         }
     }

@@ -21,12 +21,6 @@ int make_split_operand(SplitOperand* op, __half* hi, __half* lo, int64_t rows, i
     return rc;
 }
 
-// RMU_GEMM_L2PF=1 (study switch, off by default): producer warps prefetch the next row block's A boxes into L2
-static int gemm_l2_prefetch() {
-    static const int v = [] { const char* e = getenv("RMU_GEMM_L2PF"); return e ? atoi(e) : 0; }();
-    return v;
-}
-
 template <int MODE, int BN>
 static int launch_bn(const SplitOperand& A, const SplitOperand& W, const GemmParams& p, int sms, cudaStream_t st) {
     auto kern = gemm_f16x3_kernel<MODE, BN>;
@@ -63,8 +57,7 @@ bool gemm_ln_supported(const SplitOperand& W, int N) {
 }
 
 int launch_gemm_ln(const SplitOperand& A, const SplitOperand& W, const GemmLnParams& p_in, int sms, cudaStream_t st) {
-    GemmLnParams p = p_in;
-    p.l2_prefetch = gemm_l2_prefetch();
+    const GemmLnParams& p = p_in;
     if (p.M <= 0) return RMU_OK;
     if (!gemm_ln_supported(W, p.N) || p.K % kGemmBK != 0 || A.cols != p.K || W.cols != p.K || W.rows < p.N || A.rows < p.M) {
         set_error("launch_gemm_ln: shape not supported (N = 384 or 768, K % 64)");
@@ -100,8 +93,7 @@ int launch_gemm_ln(const SplitOperand& A, const SplitOperand& W, const GemmLnPar
 }
 
 int launch_gemm(int mode, const SplitOperand& A, const SplitOperand& W, const GemmParams& p_in, int sms, cudaStream_t st) {
-    GemmParams p = p_in;
-    p.l2_prefetch = gemm_l2_prefetch();
+    const GemmParams& p = p_in;
     if (p.M <= 0) return RMU_OK;
     if (p.N % 128 != 0 || p.K % kGemmBK != 0 || A.cols != p.K || W.cols != p.K || W.rows < p.N || A.rows < p.M) {
         set_error("launch_gemm: shape not supported (N % 128, K % 64)");

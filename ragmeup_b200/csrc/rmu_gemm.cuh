@@ -43,7 +43,6 @@ struct GemmParams {
     int interleave32;                     // GEMM_BIAS_SPLIT_QSCALE: out_hi is ONE buffer [M, 2N] where every 32-column group
                                           // (a d_h = 32 head) is stored as 32 hi halves followed by its 32 lo halves: a head's
                                           // q / k / v row is one 128-byte line (what attention_pair_kernel's TMA boxes fetch)
-    int l2_prefetch;                      // RMU_GEMM_L2PF=1: prefetch the next row block's A boxes into L2 one tile ahead
 };
 
 __device__ __forceinline__ void split_f16(float v, __half& hi, __half& lo) {
@@ -123,15 +122,6 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tAh, const __grid_constant
             uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
                 const int mb = tile / n_blks, nb = tile % n_blks;
-                if (p.l2_prefetch && tile + gridDim.x < tiles) {      // study switch: the next tile's A rows start in DRAM
-                    const int mb2 = (tile + gridDim.x) / n_blks;
-                    if (mb2 != mb && (tile + gridDim.x) % n_blks == 0) {      // one of the CTAs that will share that row block
-                        for (int kb = 0; kb < k_blks; ++kb) {
-                            tma_prefetch_l2_2d(&tAh, kb * kGemmBK, mb2 * kGemmBM);
-                            tma_prefetch_l2_2d(&tAl, kb * kGemmBK, mb2 * kGemmBM);
-                        }
-                    }
-                }
                 for (int kb = 0; kb < k_blks; ++kb) {
                     mbar_wait(&empty[slot], phase ^ 1);
                     uint8_t* st = smem + slot * kGemmStageBytes;
@@ -285,7 +275,6 @@ struct GemmLnParams {
     const float* gamma; const float* beta;        // [N]
     float eps;
     __half* out_hi; __half* out_lo;               // [M, N] LayerNorm output (planes)
-    int l2_prefetch;                              // as GemmParams::l2_prefetch
 };
 
 constexpr int kLnBN = 192;
@@ -368,12 +357,6 @@ gemm_f16x3_ln_kernel(const __grid_constant__ CUtensorMap tAh, const __grid_const
             int slot = 0;
             uint32_t phase = 0;
             for (int mb = cluster_id; mb < m_blks; mb += n_clusters) {
-                if (p.l2_prefetch && nb == 0 && mb + n_clusters < m_blks) {   // one CTA of the cluster warms the shared A rows
-                    for (int kb = 0; kb < k_blks; ++kb) {
-                        tma_prefetch_l2_2d(&tAh, kb * kGemmBK, (mb + n_clusters) * kGemmBM);
-                        tma_prefetch_l2_2d(&tAl, kb * kGemmBK, (mb + n_clusters) * kGemmBM);
-                    }
-                }
                 for (int kb = 0; kb < k_blks; ++kb) {
                     mbar_wait(&empty[slot], phase ^ 1);
                     uint8_t* st = smem + slot * kLnStageBytes;

@@ -41,14 +41,18 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
                  : "memory");
 }
+// suspend-time hint: the waiting thread sleeps in hardware until the phase completes (or this much time passes) instead
+// of returning to the spin loop every few hundred cycles -- in the attention kernel 40 % of all executed instructions
+// were try_wait / branch / yield of waiting warps, competing for issue slots with the softmax warps of the same sub-partition
+constexpr uint32_t kMbarSuspendHint = 0x989680u;
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
         "{\n\t.reg .pred P;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, P;\n\t}"
         : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(kMbarSuspendHint)
         : "memory");
     return ok != 0;
 }

@@ -110,6 +110,65 @@ __global__ void __launch_bounds__(160, 1) mma_cost_kernel(const Case* cases, int
     if (threadIdx.x < 32) tmem_dealloc<512>(tb);
 }
 
+// Straight-line variant: shape and operand source are template parameters, 16 MMAs per unrolled loop body (the issue
+// loop above spends ~100 cycles per MMA on its own integer work, which hides everything below that).
+template <int KIND, int N, bool TS, bool BMN>
+__global__ void __launch_bounds__(160, 1) mma_clean_kernel(long long* out) {
+    extern __shared__ __align__(1024) uint8_t sm[];
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tslot;
+    for (int i = threadIdx.x; i < 160 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(sm)[i] = 0u;
+    if (threadIdx.x == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
+    if (threadIdx.x < 32) tmem_alloc<512>(&tslot);
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tb = tslot;
+    if (threadIdx.x < 32 && elect_one()) {
+        constexpr uint32_t idesc = umma_idesc(KIND == 0 ? 0 : 2, 128, N) | (BMN ? (1u << 16) : 0u);
+        const uint32_t a_smem = smem_u32(sm), b_smem = smem_u32(sm + 64 * 1024);
+        const long long t0 = clock64();
+#pragma unroll 1
+        for (int it = 0; it < 8; ++it) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                // operands walk through distinct 16 KB A tiles / 32 KB B tiles like a K loop over 64-wide blocks does
+                const uint64_t ad = mk_desc(a_smem + (j >> 2) * 16384 + (j & 3) * 32, 1024, 2);
+                const uint64_t bd = mk_desc(b_smem + (j >> 3) * 32768 + (j & 3) * 32, 1024, 2);
+                if (TS) {
+                    if (KIND == 0) mma_f16_ts_(tb + 256, tb + (j & 7) * 8, bd, idesc, 1u);
+                    else mma_tf32_ts(tb + 256, tb + (j & 7) * 8, bd, idesc, 1u);
+                } else {
+                    if (KIND == 0) mma_f16_ss(tb + 256, ad, bd, idesc, 1u);
+                    else mma_tf32_ss(tb + 256, ad, bd, idesc, 1u);
+                }
+            }
+        }
+        const long long t1 = clock64();
+        tc_commit(&bar);
+        mbar_wait(&bar, 0);
+        const long long t2 = clock64();
+        out[0] = t1 - t0;
+        out[1] = t2 - t0;
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x < 32) tmem_dealloc<512>(tb);
+}
+
+template <int KIND, int N, bool TS, bool BMN>
+static void run_clean(long long* dout) {
+    cudaFuncSetAttribute(mma_clean_kernel<KIND, N, TS, BMN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    long long h[2];
+    for (int rep = 0; rep < 2; ++rep) mma_clean_kernel<KIND, N, TS, BMN><<<1, 160, 160 * 1024>>>(dout);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { printf("error: %s\n", cudaGetErrorString(e)); return; }
+    cudaMemcpy(h, dout, sizeof(h), cudaMemcpyDeviceToHost);
+    printf("%-6s %-4d %-3s %-5s | %8.1f      | %8.1f      | floor %d\n", KIND ? "tf32" : "f16", N, TS ? "TS" : "SS", BMN ? "MN" : "K",
+           double(h[0]) / 128, double(h[1]) / 128, N / 2);
+}
+
 int main() {
     const Case cases[] = {
         {0, 160, 0, 1, 0},   // S = Q K^T: f16 SS N=160
@@ -146,5 +205,18 @@ int main() {
     printf("TMEM round trip of one warp (cycles): idle  ld.x32+wait %lld  st.x32+wait %lld  4 x ld.x32 then one wait %lld\n", h[2 * n], h[2 * n + 1], h[2 * n + 2]);
     printf("                                      busy  ld.x32+wait %lld  st.x32+wait %lld  4 x ld.x32 then one wait %lld\n", h[2 * n + 3], h[2 * n + 4], h[2 * n + 5]);
   }
+    printf("---- straight-line issue, elect.sync, 128 MMAs: issue cyc/MMA | complete cyc/MMA\n");
+    run_clean<0, 32, false, true>(dout);
+    run_clean<0, 64, false, true>(dout);
+    run_clean<0, 160, false, false>(dout);
+    run_clean<0, 192, false, false>(dout);
+    run_clean<0, 256, false, false>(dout);
+    run_clean<0, 32, true, true>(dout);
+    run_clean<0, 64, true, true>(dout);
+    run_clean<0, 192, true, false>(dout);
+    run_clean<0, 256, true, false>(dout);
+    run_clean<1, 64, false, false>(dout);
+    run_clean<1, 128, false, false>(dout);
+    run_clean<1, 128, true, false>(dout);
     return 0;
 }
