@@ -15,7 +15,8 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libragmeup_b200.so")
 STAMP = os.path.join(CSRC, ".build_stamp")
 SOURCES = ["rmu_common.cu", "rmu_index.cu", "rmu_gemm.cu", "rmu_encoder.cu", "rmu_bm25.cu", "rmu_bm25_host.cu"]
-HEADERS = ["rmu_common.h", "rmu_ptx.cuh", "rmu_gemm.cuh", os.path.join("..", "..", "include", "ragmeup_b200.h")]
+# every header under csrc/ takes part in the up-to-date check (a list kept by hand once missed rmu_attention.cuh / rmu_scan.cuh)
+HEADERS = sorted(f for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))) + [os.path.join("..", "..", "include", "ragmeup_b200.h")]
 
 NVCC_FLAGS = [
     "-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",

@@ -389,7 +389,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tq_hi, const __grid_cons
 // warps 2 / 3 the P V issuers of head 0 / 1, then 8 softmax warps per head.
 // =====================================================================================================================
 constexpr int kApThreads = 768;                // 4 role warps + 4 output warps + 2 heads x 8 softmax warps
-constexpr int kApMaxKeys = 160;                // keys (16-aligned) + three O accumulators of 32 columns = 256 TMEM columns
+constexpr int kApMaxKeys = 160;                // keys (16-aligned); the O accumulator (64 columns) sits at column 160 of the buffer
 constexpr int kApRowB = 128;                   // operand row: two heads x 32 halves
 constexpr int kApQSlot = 2 * kAtcRows * kApRowB;   // the Q tiles (hi | lo rows) of both heads
 constexpr int kApStateBytes = 512 + 4 * 128 * 4;   // barriers | per (head, half, row) exchange slot: row max during pass 1, then the row sum
@@ -418,6 +418,10 @@ __device__ __forceinline__ void ap_add2(float& x0, float& x1, float y0, float y1
 }
 __device__ __forceinline__ void ap_sub2(float& x0, float& x1, float y0, float y1) {
     asm("{\n\t.reg .b64 a, b;\n\tmov.b64 a, {%0, %1};\n\tmov.b64 b, {%2, %3};\n\tsub.rn.f32x2 a, a, b;\n\tmov.b64 {%0, %1}, a;\n\t}"
+        : "+f"(x0), "+f"(x1) : "f"(y0), "f"(y1));
+}
+__device__ __forceinline__ void ap_mul2(float& x0, float& x1, float y0, float y1) {
+    asm("{\n\t.reg .b64 a, b;\n\tmov.b64 a, {%0, %1};\n\tmov.b64 b, {%2, %3};\n\tmul.rn.f32x2 a, a, b;\n\tmov.b64 {%0, %1}, a;\n\t}"
         : "+f"(x0), "+f"(x1) : "f"(y0), "f"(y1));
 }
 __device__ __forceinline__ void ap_split_pack(float a, float b, uint32_t& hi, uint32_t& lo) {
@@ -576,7 +580,7 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap t_qkv, const ApParams 
                 const int kvs = kvi & 1;
                 const uint32_t vg = smem_u32(kvring + kvs * kvslot + (2 + g) * kvplane);      // V rows of this head: [hi | lo]
                 const uint32_t pbase = tmem_base + g * kAtcBufCols;
-                const uint32_t d0 = pbase + OCOL, d1 = d0 + 2 * DH;   // [P_hi V_hi | P_hi V_lo] (64 columns), P_lo V_hi (32)
+                const uint32_t d0 = pbase + OCOL;                    // [P_hi V_hi + P_lo V_hi | P_hi V_lo] (64 columns)
                 const int nk16 = (S + 15) >> 4, nchunk = (S + 31) >> 5;
                 for (int r0 = 0; r0 < S; r0 += kAtcRows, ++cnt) {
                     for (int c = 0; c < nchunk; ++c) {
@@ -590,7 +594,7 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap t_qkv, const ApParams 
                             const uint64_t bv = atc_desc(vg + j16 * 16 * kApRowB, SBO, LAYOUT);
                             const uint32_t acc = j16 != 0 ? 1u : 0u;
                             mma_f16_ts(d0, a_hi, bv, IDESC_O64, acc);
-                            mma_f16_ts(d1, a_lo, bv, IDESC_O32, acc);
+                            mma_f16_ts(d0, a_lo, bv, IDESC_O32, 1u);      // N = 32: lands on the V_hi half of the same accumulator
                         }
                         ap_trace(p, 2 + g, tn, 12 + g, c);
                     }
@@ -625,16 +629,16 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap t_qkv, const ApParams 
                     if (warp_live) {
 #pragma unroll
                         for (int hc = 0; hc < 2; ++hc) {             // 16 output columns at a time
-                            uint32_t o0[16], o1[16], o2[16];
-                            tmem_ld16(ob + hc * 16, o0);
-                            tmem_ld16(ob + DH + hc * 16, o1);
-                            tmem_ld16(ob + 2 * DH + hc * 16, o2);
+                            uint32_t o0[16], o1[16];
+                            tmem_ld16(ob + hc * 16, o0);                 // (P_hi + P_lo) V_hi
+                            tmem_ld16(ob + DH + hc * 16, o1);            // P_hi V_lo
                             tmem_ld_wait();
 #pragma unroll
                             for (int j = 0; j < 8; ++j) {
-                                const float a = (__uint_as_float(o0[2 * j]) + __uint_as_float(o1[2 * j]) + __uint_as_float(o2[2 * j])) * inv;
-                                const float bq = (__uint_as_float(o0[2 * j + 1]) + __uint_as_float(o1[2 * j + 1]) + __uint_as_float(o2[2 * j + 1])) * inv;
-                                atc_split_pack(a, bq, oh[hc * 8 + j], ol[hc * 8 + j]);
+                                float a = __uint_as_float(o0[2 * j]), bq = __uint_as_float(o0[2 * j + 1]);
+                                ap_add2(a, bq, __uint_as_float(o1[2 * j]), __uint_as_float(o1[2 * j + 1]));
+                                ap_mul2(a, bq, inv, inv);
+                                ap_split_pack(a, bq, oh[hc * 8 + j], ol[hc * 8 + j]);
                             }
                         }
                     }
