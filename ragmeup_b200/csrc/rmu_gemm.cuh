@@ -64,6 +64,66 @@ __device__ __forceinline__ float erf_as(float x) {
 }
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erf_as(x * 0.70710678118654752440f)); }
 
+// Packed fp32 pairs (FFMA2 / FMUL2 / FADD2 of sm_100): one issue slot for a lane's two adjacent output columns.  The
+// FFN-in epilogue is issue-bound (ncu: 74 % of issue slots, 42 instructions per output element before this), not
+// FMA-pipe bound, so halving the count of its fp32 instructions is what pays.
+__device__ __forceinline__ float2 f2_fma(float2 a, float2 b, float2 c) {
+    float2 d;
+    asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\t"
+        "fma.rn.f32x2 rd, ra, rb, rc;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+        : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+    return d;
+}
+__device__ __forceinline__ float2 f2_mul(float2 a, float2 b) {
+    float2 d;
+    asm("{\n\t.reg .b64 ra, rb, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t"
+        "mul.rn.f32x2 rd, ra, rb;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+        : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return d;
+}
+__device__ __forceinline__ float2 f2_add(float2 a, float2 b) {
+    float2 d;
+    asm("{\n\t.reg .b64 ra, rb, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t"
+        "add.rn.f32x2 rd, ra, rb;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+        : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return d;
+}
+__device__ __forceinline__ float2 f2_sub(float2 a, float2 b) {
+    float2 d;
+    asm("{\n\t.reg .b64 ra, rb, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t"
+        "sub.rn.f32x2 rd, ra, rb;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+        : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return d;
+}
+__device__ __forceinline__ float2 f2_splat(float v) { return make_float2(v, v); }
+__device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
+// gelu_erf of two values: the same A&S 7.1.26 polynomial; the minus sign of 1 - p t e is folded into the coefficients
+__device__ __forceinline__ float2 gelu_erf2(float2 v) {
+    const float2 x = f2_mul(v, f2_splat(0.70710678118654752440f));
+    const float2 ax = make_float2(fabsf(x.x), fabsf(x.y));
+    const float2 d = f2_fma(ax, f2_splat(0.3275911f), f2_splat(1.0f));
+    const float2 t = make_float2(rcp_approx(d.x), rcp_approx(d.y));
+    float2 q = f2_fma(t, f2_splat(-1.061405429f), f2_splat(1.453152027f));      // -p
+    q = f2_fma(q, t, f2_splat(-1.421413741f));
+    q = f2_fma(q, t, f2_splat(0.284496736f));
+    q = f2_fma(q, t, f2_splat(-0.254829592f));
+    q = f2_mul(q, t);                                                           // -p t
+    float2 e = f2_mul(f2_mul(ax, ax), f2_splat(-1.4426950408889634f));          // exp(-x^2) = 2^(-x^2 log2 e)
+    e = make_float2(ex2_approx(e.x), ex2_approx(e.y));
+    const float2 y = f2_fma(q, e, f2_splat(1.0f));                              // |erf|
+    const float2 er = make_float2(copysignf(y.x, x.x), copysignf(y.y, x.y));
+    const float2 h = f2_mul(v, f2_splat(0.5f));
+    return f2_fma(h, er, h);
+}
+// (a, b) -> fp16 pair of the high parts and fp16 pair of the residuals
+__device__ __forceinline__ void split_f16x2(float2 v, __half2& hi, __half2& lo) {
+    hi = __floats2half2_rn(v.x, v.y);
+    const float2 r = f2_sub(v, __half22float2(hi));
+    lo = __floats2half2_rn(r.x, r.y);
+}
+
 // BN = output-tile width (MMA N): 128 (3 stages of 64 KB), 192 (2 x 80 KB) or 256 (2 x 96 KB).  Wider tiles read
 // the A slab once for more columns: L2->SM bytes per MMA cycle 85 -> 69 -> 62, smem operand reads 128 -> 104 -> 94.
 // The erf-GELU epilogue (FFN-in) is ALU / issue bound: with 192-wide tiles it runs 12 epilogue warps (three per
@@ -218,29 +278,24 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tAh, const __grid_constant
                     const int grow = row_base + rl;
                     if (grow < p.M) {
                         // lane = column pair: the bias is a per-lane constant of the chunk
-                        float a = stg[rl * kGemmStageRow + cp] + bia2.x, b = stg[rl * kGemmStageRow + cp + 1] + bia2.y;
-                        if (MODE == GEMM_BIAS_GELU_SPLIT) { a = gelu_erf(a); b = gelu_erf(b); }
-                        if (MODE == GEMM_BIAS_SPLIT_QSCALE) { a *= sc; b *= sc; }
+                        float2 v = f2_add(make_float2(stg[rl * kGemmStageRow + cp], stg[rl * kGemmStageRow + cp + 1]), bia2);
+                        if (MODE == GEMM_BIAS_GELU_SPLIT) v = gelu_erf2(v);
+                        if (MODE == GEMM_BIAS_SPLIT_QSCALE) v = f2_mul(v, f2_splat(sc));
                         const size_t o = static_cast<size_t>(grow) * p.N + col0 + cp;
-                        if (MODE == GEMM_BIAS_RESID_F32) {
-                            const float2 fh = __half22float2(rsh[rr >> 1]);
-                            const float2 fl = __half22float2(rsl[rr >> 1]);
-                            a += fh.x + fl.x;
-                            b += fh.y + fl.y;
-                        }
+                        if (MODE == GEMM_BIAS_RESID_F32)
+                            v = f2_add(v, f2_add(__half22float2(rsh[rr >> 1]), __half22float2(rsl[rr >> 1])));
                         if (MODE == GEMM_BIAS_F32 || MODE == GEMM_BIAS_RESID_F32) {
-                            *reinterpret_cast<float2*>(p.out_f32 + o) = make_float2(a, b);
+                            *reinterpret_cast<float2*>(p.out_f32 + o) = v;
                         } else {
-                            __half h0, l0, h1, l1;
-                            split_f16(a, h0, l0);
-                            split_f16(b, h1, l1);
+                            __half2 h2, l2;
+                            split_f16x2(v, h2, l2);
                             if (MODE == GEMM_BIAS_SPLIT_QSCALE && p.interleave32) {
                                 const size_t oi = static_cast<size_t>(grow) * (2 * p.N) + 2 * col0 + cp;   // col0 is a multiple of 32
-                                *reinterpret_cast<__half2*>(p.out_hi + oi) = __halves2half2(h0, h1);
-                                *reinterpret_cast<__half2*>(p.out_hi + oi + 32) = __halves2half2(l0, l1);
+                                *reinterpret_cast<__half2*>(p.out_hi + oi) = h2;
+                                *reinterpret_cast<__half2*>(p.out_hi + oi + 32) = l2;
                             } else {
-                                *reinterpret_cast<__half2*>(p.out_hi + o) = __halves2half2(h0, h1);
-                                *reinterpret_cast<__half2*>(p.out_lo + o) = __halves2half2(l0, l1);
+                                *reinterpret_cast<__half2*>(p.out_hi + o) = h2;
+                                *reinterpret_cast<__half2*>(p.out_lo + o) = l2;
                             }
                         }
                     }
@@ -449,10 +504,9 @@ gemm_f16x3_ln_kernel(const __grid_constant__ CUtensorMap tAh, const __grid_const
 #pragma unroll
                 for (int rr = 0; rr < 32; rr += 2) {
                     const int rl = rr + rsub;
-                    const float2 fh = __half22float2(rsh[rr >> 1]);
-                    const float2 fl = __half22float2(rsl[rr >> 1]);
-                    stg[rl * kGemmStageRow + cp] = bia2.x + (fh.x + fl.x);
-                    stg[rl * kGemmStageRow + cp + 1] = bia2.y + (fh.y + fl.y);
+                    const float2 br = f2_add(bia2, f2_add(__half22float2(rsh[rr >> 1]), __half22float2(rsl[rr >> 1])));
+                    stg[rl * kGemmStageRow + cp] = br.x;
+                    stg[rl * kGemmStageRow + cp + 1] = br.y;
                 }
                 if (cc + 1 < kChunks) load_res(row_base, cc + 1, rsh, rsl);      // in flight during the rest of this chunk
                 __syncwarp();
@@ -464,19 +518,25 @@ gemm_f16x3_ln_kernel(const __grid_constant__ CUtensorMap tAh, const __grid_const
                 const uint32_t taddr = tmem_addr(tmem_base, quad * 32, buf * kLnBN + c * 32);
                 tmem_ld32(taddr, r);
                 tmem_ld_wait();
-                float s = 0.f;
+                float2 s2 = make_float2(0.f, 0.f);                        // two interleaved partial sums (packed adds)
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const float y = __uint_as_float(r[j]) + stg[lane * kGemmStageRow + j];
-                    r[j] = __float_as_uint(y);
-                    s += y;
+                for (int j = 0; j < 32; j += 2) {
+                    const float2 y = f2_add(make_float2(__uint_as_float(r[j]), __uint_as_float(r[j + 1])),
+                                            make_float2(stg[lane * kGemmStageRow + j], stg[lane * kGemmStageRow + j + 1]));
+                    r[j] = __float_as_uint(y.x);
+                    r[j + 1] = __float_as_uint(y.y);
+                    s2 = f2_add(s2, y);
                 }
                 tmem_st32(taddr, r);
                 __syncwarp();                                            // staging tile free for the next chunk
-                const float mc = s * (1.0f / 32.0f);
-                float qc = 0.f;
+                const float mc = (s2.x + s2.y) * (1.0f / 32.0f);
+                float2 q2 = make_float2(0.f, 0.f);
 #pragma unroll
-                for (int j = 0; j < 32; ++j) { const float d = __uint_as_float(r[j]) - mc; qc = fmaf(d, d, qc); }
+                for (int j = 0; j < 32; j += 2) {
+                    const float2 d = f2_sub(make_float2(__uint_as_float(r[j]), __uint_as_float(r[j + 1])), f2_splat(mc));
+                    q2 = f2_fma(d, d, q2);
+                }
+                const float qc = q2.x + q2.y;
                 // merge (32 * cc columns: m_loc, m2) with (32 columns: mc, qc)
                 const float na = 32.0f * static_cast<float>(cc), nn = na + 32.0f;
                 const float delta = mc - m_loc;
@@ -517,21 +577,23 @@ gemm_f16x3_ln_kernel(const __grid_constant__ CUtensorMap tAh, const __grid_const
                     mbar_arrive(&acc_empty[buf]);
                 }
 #pragma unroll
-                for (int j = 0; j < 32; ++j) stg[lane * kGemmStageRow + j] = (__uint_as_float(r[j]) - mean) * rstd;
+                for (int j = 0; j < 32; j += 2) {
+                    const float2 z = f2_mul(f2_sub(make_float2(__uint_as_float(r[j]), __uint_as_float(r[j + 1])), f2_splat(mean)), f2_splat(rstd));
+                    stg[lane * kGemmStageRow + j] = z.x;
+                    stg[lane * kGemmStageRow + j + 1] = z.y;
+                }
                 __syncwarp();
 #pragma unroll
                 for (int rr = 0; rr < 32; rr += 2) {
                     const int rl = rr + rsub;
                     const int grow = row_base + rl;
                     if (grow < p.M) {
-                        const float a = stg[rl * kGemmStageRow + cp] * g2.x + b2.x;
-                        const float b = stg[rl * kGemmStageRow + cp + 1] * g2.y + b2.y;
+                        const float2 v = f2_fma(make_float2(stg[rl * kGemmStageRow + cp], stg[rl * kGemmStageRow + cp + 1]), g2, b2);
                         const size_t o = static_cast<size_t>(grow) * p.N + col0 + cp;
-                        __half h0, l0, h1, l1;
-                        split_f16(a, h0, l0);
-                        split_f16(b, h1, l1);
-                        *reinterpret_cast<__half2*>(p.out_hi + o) = __halves2half2(h0, h1);
-                        *reinterpret_cast<__half2*>(p.out_lo + o) = __halves2half2(l0, l1);
+                        __half2 h2, l2;
+                        split_f16x2(v, h2, l2);
+                        *reinterpret_cast<__half2*>(p.out_hi + o) = h2;
+                        *reinterpret_cast<__half2*>(p.out_lo + o) = l2;
                     }
                 }
                 __syncwarp();

@@ -29,12 +29,15 @@ variable is set, otherwise the collection only lives in GPU memory (said once on
 """
 from __future__ import annotations
 
+import atexit
 import glob
 import json
 import os
+import queue
 import shutil
 import sys
 import threading
+import weakref
 from typing import Any, Dict, Iterable, List, Optional, Sequence, Tuple
 
 import numpy as np
@@ -42,6 +45,9 @@ import numpy as np
 from . import _lib
 from .documents import Document, Runnable
 from .index import FlatIndex, mmr_select
+
+
+_OPEN_STORES: Dict[str, "weakref.WeakSet"] = {}     # storage directory -> live stores writing segments into it
 
 
 class B200Retriever(Runnable):
@@ -95,7 +101,15 @@ class B200VectorStore:
         self._lock = threading.RLock()
         self._storage_dir = storage_dir
         self._segments = 0
+        self._sync_writes = os.environ.get("RMU_STORE_SYNC", "0") == "1"
+        self._writer: Optional[threading.Thread] = None
+        self._queue: Optional["queue.Queue"] = None
+        self._writer_error: Optional[BaseException] = None
         if storage_dir is not None:
+            key = os.path.abspath(storage_dir)
+            for other in list(_OPEN_STORES.get(key, ())):       # another store of this process may still be writing there
+                other.flush()
+            _OPEN_STORES.setdefault(key, weakref.WeakSet()).add(self)
             if drop_old and os.path.isdir(storage_dir):
                 shutil.rmtree(storage_dir)
             self._load_segments()
@@ -170,7 +184,12 @@ class B200VectorStore:
             pks = [str(len(self._pks) + i) for i in range(n)] if ids is None else [str(i) for i in ids]
             self._insert_locked(vectors, texts, metas, pks)
             if self._storage_dir is not None:
-                self._write_segment(vectors, texts, metas, pks)
+                seg = self._segments
+                self._segments += 1
+                if self._sync_writes:
+                    self._write_segment(seg, vectors, texts, metas, pks)
+                else:
+                    self._enqueue_segment(seg, vectors, texts, metas, pks)
         return pks
 
     def add_texts(self, texts: Iterable[str], metadatas: Optional[List[dict]] = None, ids: Optional[List[str]] = None,
@@ -193,15 +212,49 @@ class B200VectorStore:
         return self.add_texts(texts, metas, ids=ids, **kwargs)
 
     # ------------------------------------------------------------------ persistence: one segment per add call
-    def _write_segment(self, vectors, texts, metas, pks) -> None:
+    # Segments are written by one background thread per store, in insertion order: the device->host copy of the vectors,
+    # the JSON table and the file write (together as long as the GPU work of a 1000-document batch) stay off the ingest
+    # loop.  ``flush()`` waits for everything queued so far and re-raises a writer error; it runs at interpreter exit, in
+    # ``save`` and before segments are re-read.  RMU_STORE_SYNC=1 writes inside ``add_*`` instead.
+    def _enqueue_segment(self, seg: int, vectors, texts, metas, pks) -> None:
+        if self._writer is None:
+            self._queue = queue.Queue(maxsize=8)             # bounds the vectors kept alive for the writer
+            self._writer = threading.Thread(target=self._writer_loop, name="rmu-segment-writer", daemon=True)
+            self._writer.start()
+            atexit.register(self.flush)
+        if self._writer_error is not None:
+            self.flush()
+        self._queue.put((seg, vectors, list(texts), [dict(m) for m in metas], list(pks)))
+
+    def _writer_loop(self) -> None:
+        while True:
+            item = self._queue.get()
+            try:
+                if item is not None and self._writer_error is None:
+                    self._write_segment(*item)
+            except BaseException as e:                       # surfaced by the next add / flush
+                self._writer_error = e
+            finally:
+                self._queue.task_done()
+            if item is None:
+                return
+
+    def flush(self) -> None:
+        """Wait until every segment queued so far is on disk."""
+        if self._writer is not None:
+            self._queue.join()
+        if self._writer_error is not None:
+            e, self._writer_error = self._writer_error, None
+            raise RuntimeError(f"segment writer failed: {e!r}") from e
+
+    def _write_segment(self, seg: int, vectors, texts, metas, pks) -> None:
         os.makedirs(self._storage_dir, exist_ok=True)
         vec = vectors if isinstance(vectors, np.ndarray) else vectors.detach().float().cpu().numpy()
         table = np.frombuffer(json.dumps({"pks": pks, "texts": texts, "metas": metas}).encode(), dtype=np.uint8)
-        path = os.path.join(self._storage_dir, f"seg_{self._segments:08d}.npz")
+        path = os.path.join(self._storage_dir, f"seg_{seg:08d}.npz")
         tmp = path + ".tmp.npz"
         np.savez(tmp, vectors=np.ascontiguousarray(vec, dtype=np.float32), metric=self.metric, table=table)
         os.replace(tmp, path)                               # a crash never leaves a half-written segment behind
-        self._segments += 1
 
     def _load_segments(self) -> None:
         files = sorted(glob.glob(os.path.join(self._storage_dir, "seg_*.npz")))
@@ -312,6 +365,7 @@ class B200VectorStore:
     # ------------------------------------------------------------------ one-file export / import
     def save(self, path: str) -> None:
         """the whole collection as one ``.npz`` (an export; the segment directory is the live persistence)"""
+        self.flush()
         with self._lock:
             vec = self.index.data().cpu().numpy() if self.index is not None else np.zeros((0, 0), np.float32)
             table = json.dumps({"pks": self._pks, "texts": self._texts, "metas": self._metas}).encode()

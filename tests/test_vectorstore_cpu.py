@@ -2,6 +2,7 @@
 persistence at ``connection_args["uri"]`` / ``drop_old`` (server/RAGHelper.py:388-394, .env.template:33),
 PGVector's upsert-on-id, locking between add and search, and the LangChain re-basing of install.py against a
 stub ``langchain_core`` whose ``VectorStore.embeddings`` is a read-only property (as the real one's is)."""
+import os
 import sys
 import threading
 import types
@@ -164,3 +165,30 @@ def test_install_rebases_on_langchain_without_touching_readonly_embeddings(numpy
     assert m.as_retriever(search_type="mmr")[0] == "lc-retriever"
     m.add_documents(_docs(2), ids=["a", "b"])
     assert len(m) == 2
+
+
+def test_background_segment_writer_flush_and_sync_mode(numpy_index, tmp_path, monkeypatch):
+    """segments are written by a background thread in insertion order; flush() makes them durable; RMU_STORE_SYNC=1 writes inline"""
+    import glob
+    uri = str(tmp_path / "bg.db")
+    a = vs.Milvus(Emb(), connection_args={"uri": uri})
+    for i in range(12):                                      # more batches than the writer queue holds
+        a.add_documents(_docs(7, 7 * i), ids=[f"k{7 * i + j}" for j in range(7)])
+    a.flush()
+    segs = sorted(glob.glob(os.path.join(a._storage_dir, "seg_*.npz")))
+    assert [os.path.basename(f) for f in segs] == [f"seg_{i:08d}.npz" for i in range(12)]
+    b = vs.Milvus(Emb(), connection_args={"uri": uri})
+    assert b._pks == a._pks and b._texts == a._texts and np.array_equal(b.index.x, a.index.x)
+    # a writer failure surfaces on the next flush instead of being lost
+    os.chmod(a._storage_dir, 0o500)
+    try:
+        a.add_documents(_docs(1, 100), ids=["late"])
+        if os.geteuid() != 0:                                # root ignores directory permissions
+            with pytest.raises(RuntimeError):
+                a.flush()
+    finally:
+        os.chmod(a._storage_dir, 0o700)
+    monkeypatch.setenv("RMU_STORE_SYNC", "1")
+    c = vs.Milvus(Emb(), connection_args={"uri": str(tmp_path / "sync.db")})
+    c.add_documents(_docs(3))
+    assert c._writer is None and len(glob.glob(os.path.join(c._storage_dir, "seg_*.npz"))) == 1

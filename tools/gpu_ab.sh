@@ -14,5 +14,5 @@ for rep in 1 2; do
 done
 cp $D/libvariant_B.so $D/libragmeup_b200.so
 timeout 300 python -m pytest tests/test_encoder_gpu.py -x -q 2>&1 | tail -2 >> $L
-RMU_ATTN_TRACE=1 PROF_B=800 timeout 200 python tools/prof_encoder.py > gpurun_out/prof_trace.log 2>&1
+
 cat $L
