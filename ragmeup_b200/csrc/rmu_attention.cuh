@@ -113,11 +113,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tq_hi, const __grid_cons
     constexpr uint32_t SBO = 8 * ROWB;                     // 8 rows (or 8 keys) per swizzle group
     constexpr int QBYTES = kAtcRows * ROWB;                // one plane of the Q tile
     constexpr int KS = DH / 16;                            // MMA K steps over d_h
-    // O accumulators sit at the end of a TMEM buffer.  With N = d_h = 32 one MMA lasts 16 cycles, far less than the
-    // tensor pipe's latency, and MMAs that accumulate into the SAME columns run back to back at that latency (measured:
-    // ~57 cycles each, 1700 cycles for the 30 MMAs of a 147-key unit, with the softmax warps waiting for O 36 % of the
-    // time).  So each product term (P_hi V_hi, P_lo V_hi, P_hi V_lo) gets its own accumulator when the columns allow it:
-    // three independent chains interleave in the pipe, and the read-out adds them up.
+    // O accumulators sit at the end of a TMEM buffer: one per product term (P_hi V_hi, P_lo V_hi, P_hi V_lo) when the
+    // columns allow it, added up by the read-out.  (Measured since: an N = 32 TS-form MMA costs 17.6 cycles and MMAs into
+    // one accumulator run at that rate, tools/micro/mma_cost.cu, so one accumulator would do as well.)
     const int OCOL = kAtcBufCols - p.nacc * DH;
     const int OCOL_C = OCOL;
     // O = P V: A from TMEM (K-major), B = V as it lies in shared memory ([key][d_h]): MN-major -> bit 16
@@ -381,12 +379,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tq_hi, const __grid_cons
 //     64-byte halves of its swizzled rows; a work item is (sequence, PAIR of adjacent heads), the two heads are the two
 //     in-flight units (TMEM buffer g = head 2*hp + g);
 //   * O = P V takes TWO MMAs per 16 keys instead of three: P_hi x [V_hi | V_lo] is one N = 64 MMA (V's row IS hi | lo),
-//     P_lo x V_hi one N = 32 MMA -- an N = 32 MMA costs the tensor pipe ~110 cycles for 16 cycles of math (its 4 KB A tile
-//     streams from TMEM), so the count of MMAs, not their width, is what a unit pays for;
+//     P_lo x V_hi one N = 32 MMA that accumulates into the V_hi half of the same 64 columns;
 //   * K and V of a work item are loaded once and serve all its query-row tiles; boxes are 32 rows, so 147 keys fetch
 //     160 rows, and a 19-row last tile fetches 32 Q rows;
 // i.e. 480 box rows per (sequence, head) instead of 2048.  Roles: warp 0 TMA, warp 1 S = Q K^T issuer (both heads),
-// warps 2 / 3 the P V issuers of head 0 / 1, then 8 softmax warps per head.
+// warps 2 / 3 the P V issuers of head 0 / 1, warps 4-7 output (O and row sums -> context planes), then 8 softmax warps
+// per head.
 // =====================================================================================================================
 constexpr int kApThreads = 768;                // 4 role warps + 4 output warps + 2 heads x 8 softmax warps
 constexpr int kApMaxKeys = 160;                // keys (16-aligned); the O accumulator (64 columns) sits at column 160 of the buffer
