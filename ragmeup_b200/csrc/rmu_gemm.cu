@@ -93,7 +93,9 @@ int launch_gemm_ln(const SplitOperand& A, const SplitOperand& W, const GemmLnPar
 }
 
 int launch_gemm(int mode, const SplitOperand& A, const SplitOperand& W, const GemmParams& p_in, int sms, cudaStream_t st) {
-    const GemmParams& p = p_in;
+    static const int ablate = [] { const char* e = getenv("RMU_GEMM_ABLATE"); return e ? atoi(e) : 0; }();
+    GemmParams p = p_in;
+    p.ablate = ablate;
     if (p.M <= 0) return RMU_OK;
     if (p.N % 128 != 0 || p.K % kGemmBK != 0 || A.cols != p.K || W.cols != p.K || W.rows < p.N || A.rows < p.M) {
         set_error("launch_gemm: shape not supported (N % 128, K % 64)");
