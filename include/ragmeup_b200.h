@@ -109,6 +109,11 @@ int rmu_topk_merge_strided(const float* scores, const int64_t* ids, int64_t rank
 int rmu_mmr_select(const float* q, const float* cand, const int32_t* n_cand, int nq, int fetch_k, int dim,
                    int k, float lambda_mult, int32_t* out_sel, void* stream);
 
+/* cosine DISTANCE (1 - cosine similarity) between consecutive rows of x [n, dim] -> out [n - 1] (device, float64):
+ * the sentence-to-sentence distances of langchain_experimental's SemanticChunker, which the reference builds at
+ * server/RAGHelper.py:329-341 and runs through text_splitter.split_documents (:368). */
+int rmu_adjacent_cosine_distance(const float* x, int64_t n, int dim, double* out, void* stream);
+
 /* ------------------------------------------------------------------ BM25 sparse leg
  * Stands behind langchain_community.retrievers.BM25Retriever (rank_bm25.BM25Okapi.get_scores /
  * get_top_n), built at server/RAGHelper.py:436-443 and queried through the EnsembleRetriever

@@ -513,6 +513,28 @@ __global__ void gather_rows_kernel(const float* __restrict__ x, long long n, int
         out[static_cast<long long>(r) * dim + d] = (row >= 0 && row < n) ? x[row * dim + d] : 0.f;
 }
 
+// SemanticChunker (langchain_experimental.text_splitter, built at server/RAGHelper.py:329-341) embeds every sentence
+// group and takes 1 - cosine_similarity of consecutive embeddings with numpy on float64 copies of the float32 vectors:
+// dot / (|a| |b|).  One warp per pair, float64 accumulation, lanes stride the row (coalesced).
+__global__ void adjacent_cosine_kernel(const float* __restrict__ x, long long pairs, int dim, double* __restrict__ out) {
+    const long long pair = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (pair >= pairs) return;
+    const unsigned lane = threadIdx.x & 31;
+    const float* a = x + pair * dim;
+    const float* b = a + dim;
+    double dot = 0.0, na = 0.0, nb = 0.0;
+    for (int j = static_cast<int>(lane); j < dim; j += 32) {
+        const double u = static_cast<double>(a[j]), v = static_cast<double>(b[j]);
+        dot = fma(u, v, dot); na = fma(u, u, na); nb = fma(v, v, nb);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        dot += __shfl_xor_sync(0xffffffffu, dot, o);
+        na += __shfl_xor_sync(0xffffffffu, na, o);
+        nb += __shfl_xor_sync(0xffffffffu, nb, o);
+    }
+    if (lane == 0) out[pair] = 1.0 - dot / (sqrt(na) * sqrt(nb));
+}
+
 // =====================================================================================================
 // greedy MMR (langchain_core.vectorstores.utils.maximal_marginal_relevance), fp64 like numpy on
 // python-float embeddings.  One CTA per query; fetch_k is small (20 by default).
@@ -1155,6 +1177,20 @@ int rmu_topk_merge(const float* scores, const int64_t* ids, int R, int nq, int k
                    int64_t* out_ids, void* stream) {
     return rmu_topk_merge_strided(scores, ids, static_cast<int64_t>(nq) * k, static_cast<int64_t>(nq) * k, R, nq, k, metric,
                                   out_scores, out_ids, stream);
+}
+
+/* cosine distance between consecutive rows (SemanticChunker: sentence group i vs i + 1), float64 like the numpy code the
+ * reference's chunker runs on the embedding lists */
+int rmu_adjacent_cosine_distance(const float* x, int64_t n, int dim, double* out, void* stream) {
+    if (!x || !out || n < 0 || dim <= 0) { set_error("rmu_adjacent_cosine_distance: bad argument"); return RMU_ERR_ARG; }
+    if (n < 2) return RMU_OK;
+    const int64_t pairs = n - 1;
+    const int warps_per_block = 8;
+    const unsigned grid = static_cast<unsigned>((pairs + warps_per_block - 1) / warps_per_block);
+    adjacent_cosine_kernel<<<grid, warps_per_block * 32, 0, static_cast<cudaStream_t>(stream)>>>(x, pairs, dim, out);
+    count_launch();
+    RMU_CHECK_LAUNCH();
+    return RMU_OK;
 }
 
 int rmu_mmr_select(const float* q, const float* cand, const int32_t* n_cand, int nq, int fetch_k, int dim, int k,

@@ -10,6 +10,7 @@
     from ScoredCrossEncoderReranker import ScoredCrossEncoderReranker        RAGHelper.py:33
     from langchain_community.retrievers import BM25Retriever                 RAGHelper.py:24
     from langchain.retrievers import ContextualCompressionRetriever, EnsembleRetriever   RAGHelper.py:10
+    from langchain_experimental.text_splitter import SemanticChunker        RAGHelper.py:27
 
 Calling ``install()`` before ``import RAGHelper_local`` registers same-named modules in
 ``sys.modules`` so those files run unchanged with ``vector_store=milvus`` (or ``postgres``).
@@ -160,5 +161,13 @@ def install() -> Dict[str, Any]:
     except Exception:
         _module("langchain.retrievers", EnsembleRetriever=c["EnsembleRetriever"],
                 ContextualCompressionRetriever=c["ContextualCompressionRetriever"])
+    # the semantic text splitter (server/RAGHelper.py:27,329-341): device embeddings + adjacent-distance kernel
+    from .chunker import SemanticChunker
+    c["SemanticChunker"] = SemanticChunker
+    try:
+        import langchain_experimental.text_splitter as lts  # type: ignore  # pragma: no cover
+        lts.SemanticChunker = SemanticChunker  # pragma: no cover
+    except Exception:
+        _module("langchain_experimental.text_splitter", SemanticChunker=SemanticChunker)
     _installed = c
     return c
