@@ -477,7 +477,8 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap t_qkv, const ApParams 
         for (int i = 0; i < 2; ++i) {
             mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 2); mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1);
             mbar_init(&s_full[i], 1); mbar_init(&o_full[i], 1); mbar_init(&s_free[i], 1);
-            mbar_init(&l_full[i], 8); mbar_init(&o_free[i], 4);
+            mbar_init(&l_full[i], 8 * 32); mbar_init(&o_free[i], 4 * 32);   // every lane arrives: compute-sanitizer racecheck
+            // models mbarrier ordering per arriving thread (an elected lane after __syncwarp is flagged on the exchange slots)
             for (int c = 0; c < kAtcMaxChunks; ++c) mbar_init(&p_full[i * kAtcMaxChunks + c], 4);   // the four warps that own the chunk
         }
         fence_mbar_init();
@@ -641,8 +642,7 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap t_qkv, const ApParams 
                         }
                     }
                     tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&o_free[g]);          // O of this head may be overwritten by the next tile's P V
+                    mbar_arrive(&o_free[g]);
                     if (warp_live && row < S) {
                         const size_t off = static_cast<size_t>(t0 + row) * p.H + (2 * hp + g) * DH;
                         uint4* dh = reinterpret_cast<uint4*>(p.ctx_hi + off);
@@ -734,8 +734,7 @@ attention_pair_kernel(const __grid_constant__ CUtensorMap t_qkv, const ApParams 
                     if (htid == 0) ap_trace(p, 4 + g + 2 * half, tn, 24 + g, c);
                 }
                 xm[r] = l0 + l1;                                 // row sum for the output warps (every warp of the head is past pass 1)
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&l_full[g]);
+                mbar_arrive(&l_full[g]);
             }
         }
     }
