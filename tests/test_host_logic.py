@@ -74,6 +74,30 @@ def test_tokenizer_ragged_matches_padded():
         assert (pt[i, :n].numpy() == typ[cu[i]:cu[i + 1]]).all()
 
 
+def test_fast_tokenisation_and_packing_equal_the_plain_path():
+    """encode_batch_fast (no offsets) and the zero-filled type ids of single texts give exactly what encode_batch +
+    per-token type ids give: truncation, ragged lengths, pairs, empty strings, unknown words"""
+    from tokenizers import Tokenizer
+    from ragmeup_b200 import tokenizer as T
+    vocab = synthetic_vocab(3000)
+    tok = build_wordpiece(vocab)
+    texts = synthetic_sentences(vocab, 60, 1, 90, seed=11) + ["", "zzzzqqqq unknownword", "a\nb  c"]
+    other = synthetic_sentences(vocab, 63, 1, 90, seed=12)
+    for max_len in (16, 64):
+        ref_tok = Tokenizer.from_str(tok.to_str())
+        ref_tok.enable_truncation(max_length=max_len, strategy="longest_first")
+        ref_tok.no_padding()
+        rt = T.RaggedTokenizer(tok, max_len)
+        for a, b in ((texts, None), (texts, other)):
+            enc = ref_tok.encode_batch(list(a) if b is None else list(zip(a, b)))
+            ids, typ, cu = rt(a, b)
+            assert cu[-1] == len(ids) == len(typ) and len(cu) == len(a) + 1
+            for i, e in enumerate(enc):
+                assert ids[cu[i]:cu[i + 1]].tolist() == e.ids and typ[cu[i]:cu[i + 1]].tolist() == e.type_ids
+    if hasattr(tok, "encode_batch_fast"):                    # the wheel in this image has it: make sure it is what runs
+        assert T._encode_batch.__doc__ and T._encode_batch(tok, ["a b"])[0].ids == tok.encode_batch(["a b"])[0].ids
+
+
 def test_weight_resolution():
     cfg, w, pooling, normalize, max_len, act, src = resolve_model("synthetic:all-MiniLM-L6-v2:3", with_head=False)
     assert (cfg.hidden, cfg.layers, cfg.heads, cfg.ffn) == (384, 6, 12, 1536) and pooling == "mean" and max_len == 256
